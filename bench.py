@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the FCOS detection hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step = one pass of the inference post-process (K1 score -> K2 top-k -> K3 NMS + clip) over one
+batch of synthetic head outputs at BASELINE config 2 (COCO 832x1344, 80 classes, batch 16 per
+GPU).  Prints ONE JSON line:
+  value     whole-job img/s with inputs resident in HBM (rotating over input sets > L2)
+  e2e       same metric through the public API (FCOSHead.detect) from pinned HOST buffers,
+            H2D of the head outputs and D2H of the detections inside the timed region
+  roofline  K1 (score_points, the kernel that moves >95 % of the bytes) timed alone with CUDA
+            events: algorithmic bytes / launch time / measured HBM peak
+  cpu_baseline  the oracle port of the reference's CPU path on this host, bounded sample
+  train     BASELINE config 3 (target assign + GIoU fwd/bwd, B=32, M<=100): us/batch + roofline
+With --impl reference the oracle port (the reference is pure Python and does not travel to the
+GPU box; the port is pinned against it by tests/golden) is timed on the host cores instead.
+Multi-GPU (torchrun): batch sharded by rank (weak scaling, 16 images per GPU), one final NCCL
+all_gather of the padded detections per step; time = max over ranks.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from pytorch_object_detection_b200 import workloads as W  # noqa: E402
+
+BATCH = 16
+NCLS = 80
+MAX_BOX = 1000
+SCORE_THR = 0.05
+NMS_THR = 0.6
+TRAIN_BATCH = 32
+TRAIN_MAX_GT = 100
+P = W.num_points(W.COCO_LEVELS)
+WORKLOAD = f"COCO 832x1344 FCOS post-process (score+top-k {MAX_BOX}+NMS {NMS_THR}+clip), {NCLS} classes, " \
+           f"P={P}, batch {BATCH} per GPU"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while timed regions run."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        self._active.set()
+        return self
+
+    def __exit__(self, *a):
+        self._active.clear()
+
+    def summary(self):
+        self._stop.set()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "samples": len(s),
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_reference_leg(steps, warmup, sample_images):
+    """The reference's CPU path (oracle port) on a bounded sample of the same workload."""
+    from oracle import fcos_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = W.head_outputs(sample_images, NCLS, W.COCO_LEVELS, seed=1000)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        dets = O.detect(x, SCORE_THR, NMS_THR, MAX_BOX, W.STRIDES)
+        for d in dets:
+            O.clip_boxes_(d[2], *W.COCO_HW)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": sample_images * len(times) / total, "unit": "img/s", "cores": torch.get_num_threads(),
+            "kind": "port", "ms_per_step": 1e3 * total / len(times),
+            "sample": f"{sample_images} images of the workload per step x {len(times)} steps, oracle port "
+                      f"(torch CPU ops + numpy NMS), {torch.get_num_threads()} torch threads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sets", type=int, default=4, help="input sets rotated through (each 127 MB; L2 is 126 MB)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = min(args.steps, 20)
+        leg = cpu_reference_leg(steps, min(warmup, 2), 4)
+        line = {"impl": "reference", "metric": "postprocess_throughput", "value": leg["value"], "unit": "img/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": min(warmup, 2), "ms_per_step": leg["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": WORKLOAD, "sample": leg["sample"]},
+                "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": leg["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU: b200det has no CPU path"
+    import pytorch_object_detection_b200 as B
+    from pytorch_object_detection_b200 import ops
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic inputs: `sets` independent batches, rotated so every step misses L2 -------
+    host_sets = [W.head_outputs(BATCH, NCLS, W.COCO_LEVELS, seed=2000 + 17 * rank + s) for s in range(args.sets)]
+    dev_sets = [[[t.to(dev) for t in part] for part in hs] for hs in host_sets]
+    in_bytes = sum(t.numel() * 4 for part in host_sets[0] for t in part)
+    head = B.FCOSHead(SCORE_THR, NMS_THR, MAX_BOX, W.STRIDES)
+    sampler = ClockSampler(local)
+
+    def gather(outs):
+        if dist is None:
+            return
+        for t in outs:
+            full = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            dist.all_gather_into_tensor(full, t.contiguous())
+
+    def step(i):
+        outs = head.detect(dev_sets[i % args.sets], clip_hw=W.COCO_HW)
+        gather(outs)
+        return outs
+
+    # ---- value: device-resident ---------------------------------------------------------------
+    for i in range(warmup):
+        step(i)
+    barrier()
+    l0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler:
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+    launches = ops.launch_count - l0
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    ms_per_step = ms / args.steps
+    value = world * BATCH / (ms_per_step * 1e-3)
+
+    # ---- e2e: pinned host inputs -> H2D -> public API -> D2H of the detections -----------------
+    pinned = [[[t.pin_memory() for t in part] for part in hs] for hs in host_sets[:2]]
+    stage = [[torch.empty_like(t, device=dev) for t in part] for part in host_sets[0]]
+    e2e_steps = max(3, min(args.steps, 30))
+    d2h_bytes = 0
+
+    def e2e_step(i):
+        nonlocal d2h_bytes
+        src = pinned[i % len(pinned)]
+        for ps, pd in zip(src, stage):
+            for a, b in zip(ps, pd):
+                b.copy_(a, non_blocking=True)
+        s, c, bx, n = head.detect(stage, clip_hw=W.COCO_HW)
+        gather((s, c, bx, n))
+        res = [t.cpu() for t in (s, c, bx, n)]     # blocking D2H of the step's result
+        d2h_bytes = sum(t.numel() * t.element_size() for t in res)
+        return res
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    with sampler:
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            e2e_step(i)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_value = world * BATCH * e2e_steps / e2e_s
+
+    # ---- roofline of the dominant kernel (K1) timed alone, same inputs, same rotation ----------
+    peak, peak_src = peaks()
+    k1_bytes = BATCH * P * ((NCLS + 1) * 4 + 4 + 2)       # cls + cnt planes read, score f32 + class i16 written
+    for i in range(warmup):
+        ops.score_points(dev_sets[i % args.sets][0], dev_sets[i % args.sets][1], W.STRIDES)
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with sampler:
+        for i, (a, b) in enumerate(evs):
+            a.record()
+            ops.score_points(dev_sets[i % args.sets][0], dev_sets[i % args.sets][1], W.STRIDES)
+            b.record()
+        torch.cuda.synchronize()
+    k1_ms = sorted(a.elapsed_time(b) for a, b in evs)
+    k1_avg = sum(k1_ms) / len(k1_ms)
+    achieved = k1_bytes / (k1_avg * 1e-3) / 1e9
+    roofline = {"kernel": "score_points_kernel (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": k1_bytes, "us_per_launch": 1e3 * k1_avg, "us_median": 1e3 * k1_ms[len(k1_ms) // 2]}
+
+    # ---- training side (config 3): target assignment + GIoU fwd/bwd ---------------------------
+    train = None
+    if rank == 0:
+        gt, labels = W.gt_boxes(TRAIN_BATCH, TRAIN_MAX_GT, W.COCO_HW, NCLS, seed=3000)
+        gt, labels = gt.to(dev), labels.to(dev)
+        regs = [[torch.exp(torch.randn(TRAIN_BATCH, 4, h, w, device=dev) + 3).requires_grad_(True)
+                 for h, w in W.COCO_LEVELS] for _ in range(4)]
+        gen = B.FCOSGenTargets(W.STRIDES, W.HISFCOS_RANGES)
+        fake = [torch.empty(TRAIN_BATCH, 1, h, w, device="meta") for h, w in W.COCO_LEVELS]
+
+        def train_step(i):
+            tgt = gen([[fake, fake, fake], gt, labels])
+            loss = B.compute_reg_loss(regs[i % 4], tgt[2], None, "giou", _mask_src=tgt[1]).mean()
+            loss.backward()
+            return loss
+
+        for i in range(warmup):
+            train_step(i)
+        torch.cuda.synchronize()
+        n_tr = args.steps
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with sampler:
+            a.record()
+            for i in range(n_tr):
+                train_step(i)
+            b.record()
+            torch.cuda.synchronize()
+        us = 1e3 * a.elapsed_time(b) / n_tr
+        # assign alone, for its own roofline: 28 bytes written per point
+        a.record()
+        for i in range(n_tr):
+            ops.assign_targets(W.COCO_LEVELS, W.STRIDES, W.HISFCOS_RANGES, gt, labels)
+        b.record()
+        torch.cuda.synchronize()
+        us_assign = 1e3 * a.elapsed_time(b) / n_tr
+        assign_bytes = TRAIN_BATCH * P * 28 + TRAIN_BATCH * TRAIN_MAX_GT * 24
+        train = {"workload": f"target assign + GIoU loss fwd+bwd, COCO 832x1344, B={TRAIN_BATCH}, M<={TRAIN_MAX_GT}",
+                 "us_per_batch": us, "assign_us": us_assign, "assign_bytes": assign_bytes,
+                 "assign_gbs": assign_bytes / (us_assign * 1e-6) / 1e9,
+                 "assign_frac_of_peak": assign_bytes / (us_assign * 1e-6) / 1e9 / peak}
+
+    clocks = sampler.summary()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    cpu = cpu_reference_leg(steps=6, warmup=1, sample_images=4)
+    line = {"metric": "postprocess_throughput", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * BATCH,
+                       "l2": f"{args.sets} input sets of {in_bytes / 1e6:.0f} MB rotated (> 126 MB L2)",
+                       "collective": "all_gather of padded detections per step" if world > 1 else "none"},
+            "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "steps": e2e_steps, "api": "FCOSHead.detect(clip_hw=...) on pinned host inputs"},
+            "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "train": train, "clocks": clocks}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,166 @@
+/*
+ * b200det — C ABI of the B200-native (sm_100a) FCOS detection hot path.
+ *
+ * The reference (hby1320/pytorch_object_detection) is pure Python and has no FFI layer;
+ * its boundary is the call signatures of four nn.Modules.  Every entry point below names
+ * the reference interface it replaces (paths relative to the reference tree).  The Python
+ * host side (pytorch_object_detection_b200/head.py, loss.py) binds these with ctypes and
+ * mirrors those modules; INTEGRATION.md shows the stub a maintainer of the reference adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; the library never allocates,
+ *     frees or synchronises; all work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - tensors are dense row-major ("contiguous") in the shapes given; level maps are NCHW fp32.
+ *   - return value: 0 = ok, otherwise a b200det_status; b200det_status_string() names it.
+ *   - no CPU implementation exists behind this ABI.
+ */
+#ifndef B200DET_H_
+#define B200DET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DET_ABI_VERSION 2
+#define B200DET_MAX_LEVELS 8
+#define B200DET_MAX_BOX 8192      /* largest max_detection_box / NMS candidate count per image */
+
+typedef enum {
+  B200DET_OK = 0,
+  B200DET_ERR_ARG = 1,            /* null pointer, non-positive size, too many levels ... */
+  B200DET_ERR_UNSUPPORTED = 2,    /* size or dtype outside what the kernels cover */
+  B200DET_ERR_WORKSPACE = 3,      /* workspace smaller than *_workspace_bytes() */
+  B200DET_ERR_CUDA = 4            /* a launch failed; see b200det_last_cuda_error() */
+} b200det_status;
+
+/* One FPN level of head outputs: cls [B,C,h,w], cnt [B,1,h,w], reg [B,4,h,w], fp32 (any may
+ * be NULL where an entry point does not read it).  `stride` is the level's pixel stride; the
+ * point grid (j*stride + stride/2, i*stride + stride/2) of utill/utills.py:58-73 is computed
+ * in-kernel, never materialised.  Points are numbered level-major, row-major inside a level
+ * (the order reshape_cat_out produces, head.py:8-26); P = sum(h*w). */
+typedef struct {
+  const void* cls;
+  const void* cnt;
+  const void* reg;
+  int32_t h, w, stride, pad_;
+} b200det_level;
+
+int         b200det_abi_version(void);
+const char* b200det_status_string(int status);
+const char* b200det_last_cuda_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Inference post-processing.  Replaces FCOSHead.forward + ClipBoxes.forward
+ * (model/modules/head.py:52-102, 152-162; call sites test.py:206-207, Test_coco.py:141-142).
+ * ------------------------------------------------------------------------------------- */
+
+/* K1 — head.py:8-26,57-63 without the NHWC copy: per point
+ *   score = sqrt(max_c sigmoid(cls) * sigmoid(cnt)),  cls0 = argmax_c (first index on ties),
+ * written level-major as score[B,P] f32 and cls0[B,P] int16 (0-based). */
+int b200det_score_points(const b200det_level* levels, int n_levels, int batch, int num_classes,
+                         float* score, int16_t* cls0, void* stream);
+
+/* K2 — head.py:69-80 + the threshold of head.py:90: per image the k = min(max_box, P) highest
+ * scores that are >= score_thr, sorted (score desc, point index asc), gathered to
+ *   cand_score[B,max_box] f32, cand_cls[B,max_box] i32 (1-based), cand_box[B,max_box,4] f32
+ *   (x-l, y-t, x+r, y+b; head.py:29-38), cand_point[B,max_box] i32, cand_count[B] i32. */
+int b200det_select_topk(const b200det_level* levels, int n_levels, int batch,
+                        const float* score, const int16_t* cls0, float score_thr, int max_box,
+                        float* cand_score, int32_t* cand_cls, float* cand_box,
+                        int32_t* cand_point, int32_t* cand_count, void* stream);
+
+/* K3 — torchvision.ops.batched_nms as called at head.py:94, CPU semantics of torchvision
+ * 0.26.0: count*4 <= 4000 -> coordinate trick (boxes + cls*(max_coord+1), all pairs);
+ * otherwise per-class NMS on raw boxes.  Greedy, stable descending score order, fp32
+ * IoU = inter / (area_i + area_j - inter) without FMA, suppressed when (double)IoU > nms_thr.
+ * Input: per image `in_count[b]` (or `n` when in_count is NULL) candidates, row stride `n`;
+ * only those with score >= score_thr take part (head.py:90-93).  n <= B200DET_MAX_BOX.
+ * Output, in keep order: out_score[B,n] f32, out_cls[B,n] i64, out_box[B,n,4] f32,
+ * out_keep[B,n] i64 (index into the thresholded candidate list, as batched_nms returns),
+ * out_count[B] i32.  If clip_h > 0 the boxes are clamped to [0,clip_w-1]x[0,clip_h-1]
+ * (ClipBoxes, head.py:152-162) while they are written. */
+size_t b200det_nms_workspace_bytes(int batch, int n);
+int b200det_batched_nms(int batch, int n, const float* boxes, const float* scores,
+                        const int64_t* classes, const int32_t* in_count,
+                        float score_thr, double nms_thr, int clip_h, int clip_w,
+                        void* workspace, size_t workspace_bytes,
+                        float* out_score, int64_t* out_cls, float* out_box, int64_t* out_keep,
+                        int32_t* out_count, void* stream);
+
+/* K1 + K2 + K3 on one stream: the whole of FCOSHead.forward (+ ClipBoxes when clip_h > 0).
+ * Outputs have row stride max_box.  out_keep holds indices into the image's top-k list. */
+size_t b200det_postprocess_workspace_bytes(int batch, int num_points, int max_box);
+int b200det_postprocess(const b200det_level* levels, int n_levels, int batch, int num_classes,
+                        float score_thr, double nms_thr, int max_box,
+                        int clip_h, int clip_w, void* workspace, size_t workspace_bytes,
+                        float* out_score, int64_t* out_cls, float* out_box, int64_t* out_keep,
+                        int32_t* out_count, void* stream);
+
+/* ClipBoxes.forward (head.py:152-162): in-place clamp of boxes[n_boxes,4]. */
+int b200det_clip_boxes(float* boxes, int64_t n_boxes, int img_h, int img_w, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Training targets.  Replaces FCOSGenTargets.forward / generate_target
+ * (model/modules/head.py:218-316; call site train.py:177).
+ * ------------------------------------------------------------------------------------- */
+
+/* level_hw[2*l] = h, level_hw[2*l+1] = w; limit_lo/hi[l] = lim_range of level l (as fp32);
+ * radius_px[l] = stride * sample_radio_ratio (as fp32);
+ * gt_boxes [B,M,4] f32 (x0,y0,x1,y1; padding rows -1), gt_labels [B,M] i64.
+ * Outputs, level-major over P = sum(h*w): cls_t [B,P] i64 (0 = background),
+ * cnt_t [B,P] f32 (-1 = negative), reg_t [B,P,4] f32 (l,t,r,b; -1 = negative),
+ * gt_index [B,P] i32 (assigned GT row, -1 = negative; may be NULL). */
+int b200det_assign_targets(const int32_t* level_hw, const int32_t* strides,
+                           const float* limit_lo, const float* limit_hi, const float* radius_px,
+                           int n_levels, int batch, int max_gt,
+                           const float* gt_boxes, const int64_t* gt_labels,
+                           int64_t* cls_t, float* cnt_t, float* reg_t, int32_t* gt_index,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Losses.  Replace compute_reg_loss / compute_cnt_loss / compute_cls_loss and their
+ * autograd backward (model/loss.py:6-57, 116-193; call site train.py:178-180).
+ * `cnt_t` [B,P] f32 is the positive mask source: a point is positive iff cnt_t > -1
+ * (loss.py:205); FCOSLoss passes the centerness target itself.
+ * Every forward writes loss[B] f32 = (sum over the image) / num_pos[b] and
+ * num_pos[B] f32 = clamp(count(cnt_t > -1), 1), as loss.py:26,57,139.  Every backward takes
+ * grad_loss[B] f32 = dL/d(loss[b]) and writes the gradient of every level map in its own
+ * NCHW layout (zeros where the reference's gradient is zero).
+ * ------------------------------------------------------------------------------------- */
+
+/* mode: 0 = 'iou' (loss.py:142-152), 1 = 'giou' (loss.py:155-177).  Reads levels[].reg. */
+int b200det_box_loss_fwd(const b200det_level* levels, int n_levels, int batch,
+                         const float* cnt_t, const float* reg_t, int mode,
+                         float* loss, float* num_pos, void* stream);
+/* grads[l] = d/d(reg level l) [B,4,h,w]. */
+int b200det_box_loss_bwd(const b200det_level* levels, float* const* grads, int n_levels, int batch,
+                         const float* cnt_t, const float* reg_t, int mode,
+                         const float* grad_loss, const float* num_pos, void* stream);
+
+/* Centerness BCE-with-logits over positives (loss.py:29-57).  Reads levels[].cnt;
+ * cnt_target [B,P] f32 holds the BCE targets (normally the same pointer as cnt_t). */
+int b200det_cnt_loss_fwd(const b200det_level* levels, int n_levels, int batch,
+                         const float* cnt_t, const float* cnt_target,
+                         float* loss, float* num_pos, void* stream);
+int b200det_cnt_loss_bwd(const b200det_level* levels, float* const* grads, int n_levels, int batch,
+                         const float* cnt_t, const float* cnt_target, const float* grad_loss,
+                         const float* num_pos, void* stream);
+
+/* Focal loss over ALL points (loss.py:6-26,180-193; alpha 0.25, gamma 2).  Reads levels[].cls.
+ * workspace: b200det_cls_loss_workspace_bytes(). */
+size_t b200det_cls_loss_workspace_bytes(int batch, int num_points);
+int b200det_cls_loss_fwd(const b200det_level* levels, int n_levels, int batch, int num_classes,
+                         const int64_t* cls_t, const float* cnt_t,
+                         void* workspace, size_t workspace_bytes,
+                         float* loss, float* num_pos, void* stream);
+int b200det_cls_loss_bwd(const b200det_level* levels, float* const* grads, int n_levels, int batch,
+                         int num_classes, const int64_t* cls_t,
+                         const float* grad_loss, const float* num_pos, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DET_H_ */

@@ -1,0 +1,163 @@
+// K4a — FCOS target assignment (FCOSGenTargets.generate_target, model/modules/head.py:235-316).
+//
+// The reference materialises [B, HW, M, 4] offsets and reduces over M.  Here a CTA owns 512
+// consecutive points of one level of one image.  The centre-sampling mask
+// (max(|x-cx|, |y-cy|) < 1.5*stride, head.py:275-283) means only ground-truth boxes whose centre
+// row lies within 1.5 strides of the tile's rows can be positive for it, so the CTA first
+// gathers those few boxes into shared memory (a conservative, rounding-safe pre-filter) and every
+// point then evaluates the reference's exact fp32 expressions against that short list:
+//   l = x-x0, t = y-y0, r = x1-x, b = y1-y;  area = (l+r)*(t+b)            head.py:261-268
+//   positive iff min(l,t,r,b) > 0, lo < max(l,t,r,b) <= hi, centre mask    head.py:272-283
+//   winner = smallest area, lowest GT index on ties (torch.min's first index; head.py:285-286)
+//   centerness = sqrt(min(l,r)*min(t,b) / (max(l,r)*max(t,b) + 1e-10))      head.py:294-299
+//   no positive -> (0, -1, -1)                                             head.py:308-314
+// The kernel is a pure, fully coalesced write stream: 28 (+4) bytes per point, nothing re-read.
+// (A positive box with area >= 99999999 px^2 would lose to the reference's sentinel; images are
+// far smaller than 10^4 x 10^4, so that case is not modelled.)
+#include "common.cuh"
+
+namespace b200det {
+namespace {
+
+struct AssignTable {
+  int h[B200DET_MAX_LEVELS], w[B200DET_MAX_LEVELS], stride[B200DET_MAX_LEVELS], hw[B200DET_MAX_LEVELS];
+  int point_off[B200DET_MAX_LEVELS + 1], tile_off[B200DET_MAX_LEVELS + 1];
+  float lo[B200DET_MAX_LEVELS], hi[B200DET_MAX_LEVELS], radius[B200DET_MAX_LEVELS];
+  int n_levels, num_points;
+};
+
+struct GtEntry {
+  float x0, y0, x1, y1;
+  int idx;
+};
+
+__global__ void __launch_bounds__(kTileThreads)
+assign_targets_kernel(const AssignTable at, const int M, const float* __restrict__ gt_boxes,
+                      const long long* __restrict__ gt_labels, long long* __restrict__ cls_t,
+                      float* __restrict__ cnt_t, float* __restrict__ reg_t, int32_t* __restrict__ gt_index) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GtEntry* list = reinterpret_cast<GtEntry*>(smem_raw);
+  __shared__ int s_n;
+
+  const int b = blockIdx.y;
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < B200DET_MAX_LEVELS; ++i) l += (i < at.n_levels && (int)blockIdx.x >= at.tile_off[i]) ? 1 : 0;
+  const int hw = at.hw[l], w = at.w[l], s = at.stride[l];
+  const int t0 = (blockIdx.x - at.tile_off[l]) * kTile;
+  const int t1 = min(t0 + kTile, hw) - 1;
+  const float lo = at.lo[l], hi = at.hi[l], radius = at.radius[l];
+  const int half = s / 2;
+
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  {
+    // rows covered by this tile -> y range; keep boxes whose centre row can pass the centre mask.
+    // The margin of 1 px dwarfs any fp32 rounding of (y0+y1)/2 or y-cy at image-scale coordinates.
+    const float ymin = (float)((t0 / w) * s + half) - radius - 1.0f;
+    const float ymax = (float)((t1 / w) * s + half) + radius + 1.0f;
+    const float4* g4 = reinterpret_cast<const float4*>(gt_boxes) + (size_t)b * M;
+    for (int m = threadIdx.x; m < M; m += kTileThreads) {
+      const float4 g = g4[m];
+      const float cy = __fmul_rn(__fadd_rn(g.y, g.w), 0.5f);
+      if (cy >= ymin && cy <= ymax) {
+        const int at_ = atomicAdd(&s_n, 1);
+        list[at_] = GtEntry{g.x, g.y, g.z, g.w, m};
+      }
+    }
+  }
+  __syncthreads();
+  const int n_list = s_n;
+
+  const size_t out0 = (size_t)b * at.num_points + at.point_off[l];
+#pragma unroll
+  for (int q = 0; q < kTilePts; ++q) {
+    const int pos = t0 + threadIdx.x + q * kTileThreads;    // strided: every store instruction is coalesced
+    if (pos >= hw) break;
+    const float x = (float)((pos % w) * s + half);
+    const float y = (float)((pos / w) * s + half);
+    float best_area = CUDART_INF_F;
+    int best_m = -1;
+    float bl = -1.f, bt = -1.f, br = -1.f, bb = -1.f;
+    for (int e = 0; e < n_list; ++e) {
+      const GtEntry g = list[e];
+      const float lf = __fsub_rn(x, g.x0), tf = __fsub_rn(y, g.y0);
+      const float rf = __fsub_rn(g.x1, x), bf = __fsub_rn(g.y1, y);
+      const float omin = fminf(fminf(lf, tf), fminf(rf, bf));
+      const float omax = fmaxf(fmaxf(lf, tf), fmaxf(rf, bf));
+      const float cx = __fmul_rn(__fadd_rn(g.x0, g.x1), 0.5f);
+      const float cy = __fmul_rn(__fadd_rn(g.y0, g.y1), 0.5f);
+      const float cmax = fmaxf(fmaxf(__fsub_rn(x, cx), __fsub_rn(y, cy)), fmaxf(__fsub_rn(cx, x), __fsub_rn(cy, y)));
+      const bool pos_ok = (omin > 0.f) && (omax > lo) && (omax <= hi) && (cmax < radius);
+      if (pos_ok) {
+        const float area = __fmul_rn(__fadd_rn(lf, rf), __fadd_rn(tf, bf));
+        if (area < best_area || (area == best_area && g.idx < best_m)) {
+          best_area = area;
+          best_m = g.idx;
+          bl = lf; bt = tf; br = rf; bb = bf;
+        }
+      }
+    }
+    long long label = 0;
+    float cnt = -1.f;
+    if (best_m >= 0) {
+      label = gt_labels[(size_t)b * M + best_m];
+      const float lr_min = fminf(bl, br), lr_max = fmaxf(bl, br);
+      const float tb_min = fminf(bt, bb), tb_max = fmaxf(bt, bb);
+      cnt = __fsqrt_rn(__fdiv_rn(__fmul_rn(lr_min, tb_min), __fadd_rn(__fmul_rn(lr_max, tb_max), 1e-10f)));
+    }
+    const size_t o = out0 + pos;
+    stg_stream_s64(cls_t + o, label);
+    stg_stream_f1(cnt_t + o, cnt);
+    stg_stream_f4(reg_t + 4 * o, make_float4(bl, bt, br, bb));
+    if (gt_index) gt_index[o] = best_m;
+  }
+}
+
+}  // namespace
+}  // namespace b200det
+
+extern "C" int b200det_assign_targets(const int32_t* level_hw, const int32_t* strides, const float* limit_lo,
+                                      const float* limit_hi, const float* radius_px, int n_levels, int batch,
+                                      int max_gt, const float* gt_boxes, const int64_t* gt_labels, int64_t* cls_t,
+                                      float* cnt_t, float* reg_t, int32_t* gt_index, void* stream) {
+  using namespace b200det;
+  if (!level_hw || !strides || !limit_lo || !limit_hi || !radius_px || n_levels <= 0 ||
+      n_levels > B200DET_MAX_LEVELS || batch <= 0 || batch > 65535 || max_gt < 0 || !cls_t || !cnt_t || !reg_t)
+    return B200DET_ERR_ARG;
+  if (max_gt > 0 && (!gt_boxes || !gt_labels)) return B200DET_ERR_ARG;
+  if (!aligned16(gt_boxes) || !aligned16(reg_t)) return B200DET_ERR_ARG;
+  const size_t smem = (size_t)max_gt * sizeof(GtEntry);
+  if (smem > 200 * 1024) return B200DET_ERR_UNSUPPORTED;
+  AssignTable at;
+  long long off = 0;
+  int toff = 0;
+  for (int l = 0; l < B200DET_MAX_LEVELS; ++l) {
+    const bool on = l < n_levels;
+    if (on && (level_hw[2 * l] <= 0 || level_hw[2 * l + 1] <= 0 || strides[l] <= 0)) return B200DET_ERR_ARG;
+    at.h[l] = on ? level_hw[2 * l] : 0;
+    at.w[l] = on ? level_hw[2 * l + 1] : 0;
+    at.stride[l] = on ? strides[l] : 0;
+    at.hw[l] = at.h[l] * at.w[l];
+    at.lo[l] = on ? limit_lo[l] : 0.f;
+    at.hi[l] = on ? limit_hi[l] : 0.f;
+    at.radius[l] = on ? radius_px[l] : 0.f;
+    at.point_off[l] = (int)off;
+    at.tile_off[l] = toff;
+    off += at.hw[l];
+    toff += (at.hw[l] + kTile - 1) / kTile;
+    if (off > (1ll << 30)) return B200DET_ERR_ARG;
+  }
+  at.point_off[B200DET_MAX_LEVELS] = (int)off;
+  at.tile_off[B200DET_MAX_LEVELS] = toff;
+  at.n_levels = n_levels;
+  at.num_points = (int)off;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(assign_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
+  }
+  assign_targets_kernel<<<dim3(toff, batch), kTileThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      at, max_gt, gt_boxes, reinterpret_cast<const long long*>(gt_labels), reinterpret_cast<long long*>(cls_t), cnt_t,
+      reg_t, gt_index);
+  return check_launch();
+}

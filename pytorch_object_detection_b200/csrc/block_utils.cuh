@@ -1,0 +1,80 @@
+// CTA-wide primitives used by the select / NMS kernels: scans, reductions, bitonic sort.
+#pragma once
+#include "common.cuh"
+
+namespace b200det {
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// Exclusive scan of one int per thread over the whole CTA (blockDim.x multiple of 32, <= 1024).
+// `warp_sums` is 33 ints of shared scratch.  Returns the exclusive prefix; *total gets the sum.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  __syncthreads();  // protect warp_sums from a previous use
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int s = lane < nwarps ? warp_sums[lane] : 0;
+    int si = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int o = __shfl_up_sync(0xffffffffu, si, d);
+      if (lane >= d) si += o;
+    }
+    warp_sums[lane] = si - s;            // exclusive warp offsets
+    if (lane == 31) warp_sums[32] = si;  // grand total
+  }
+  __syncthreads();
+  *total = warp_sums[32];
+  return warp_sums[warp] + incl - v;
+}
+
+__device__ __forceinline__ float block_max(float v, float* scratch /*32 floats*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float r = scratch[0];
+  for (int i = 1; i < nwarps; ++i) r = fmaxf(r, scratch[i]);
+  return r;
+}
+
+// In-place DESCENDING bitonic sort of n (power of two) 64-bit keys in shared memory.
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long* buf, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+        // t-th compare-exchange pair of this stage: insert a 0 bit at position log2(j)
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i | j;
+        const unsigned long long a = buf[i], b = buf[p];
+        const bool desc = (i & k) == 0;
+        if (desc ? (a < b) : (a > b)) {
+          buf[i] = b;
+          buf[p] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace b200det

@@ -1,0 +1,142 @@
+// Shared device/host helpers for the b200det kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/b200det.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "b200det is written for sm_100a (B200) only"
+#endif
+
+namespace b200det {
+
+constexpr int kTileThreads = 128;        // streaming kernels: 128 threads x 4 points
+constexpr int kTilePts = 4;
+constexpr int kTile = kTileThreads * kTilePts;   // 512 points of one level of one image per CTA
+constexpr int kNmsTile = 64;             // boxes per NMS mask word
+
+// Kernel-side level table (passed by value in kernel params).
+struct LevelTable {
+  const float* cls[B200DET_MAX_LEVELS];
+  const float* cnt[B200DET_MAX_LEVELS];
+  const float* reg[B200DET_MAX_LEVELS];
+  int h[B200DET_MAX_LEVELS];
+  int w[B200DET_MAX_LEVELS];
+  int stride[B200DET_MAX_LEVELS];
+  int hw[B200DET_MAX_LEVELS];
+  int vec_ok[B200DET_MAX_LEVELS];          // hw % 4 == 0 and every map pointer 16-byte aligned
+  int point_off[B200DET_MAX_LEVELS + 1];   // prefix sum of hw (level-major point index)
+  int tile_off[B200DET_MAX_LEVELS + 1];    // prefix sum of ceil(hw / kTile)
+  int n_levels;
+  int num_points;
+};
+
+// Gradient destinations, one per level (same NCHW shape as the map they belong to).
+struct GradTable {
+  float* g[B200DET_MAX_LEVELS];
+};
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Returns false on bad arguments.
+inline bool make_level_table(const b200det_level* levels, int n_levels, LevelTable* t) {
+  if (!levels || n_levels <= 0 || n_levels > B200DET_MAX_LEVELS) return false;
+  long long off = 0;
+  int toff = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    if (levels[l].h <= 0 || levels[l].w <= 0 || levels[l].stride <= 0) return false;
+    t->cls[l] = static_cast<const float*>(levels[l].cls);
+    t->cnt[l] = static_cast<const float*>(levels[l].cnt);
+    t->reg[l] = static_cast<const float*>(levels[l].reg);
+    t->h[l] = levels[l].h;
+    t->w[l] = levels[l].w;
+    t->stride[l] = levels[l].stride;
+    t->hw[l] = levels[l].h * levels[l].w;
+    t->vec_ok[l] = (t->hw[l] % 4 == 0) && aligned16(levels[l].cls) && aligned16(levels[l].cnt) &&
+                   aligned16(levels[l].reg);
+    t->point_off[l] = static_cast<int>(off);
+    t->tile_off[l] = toff;
+    off += t->hw[l];
+    toff += (t->hw[l] + kTile - 1) / kTile;
+    if (off > (1ll << 30)) return false;
+  }
+  for (int l = n_levels; l <= B200DET_MAX_LEVELS; ++l) {
+    t->point_off[l] = static_cast<int>(off);
+    t->tile_off[l] = toff;
+  }
+  for (int l = n_levels; l < B200DET_MAX_LEVELS; ++l) {
+    t->cls[l] = t->cnt[l] = t->reg[l] = nullptr;
+    t->h[l] = t->w[l] = t->stride[l] = t->hw[l] = t->vec_ok[l] = 0;
+  }
+  t->n_levels = n_levels;
+  t->num_points = static_cast<int>(off);
+  return true;
+}
+
+void set_cuda_error(cudaError_t e);
+
+inline int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_cuda_error(e);
+    return B200DET_ERR_CUDA;
+  }
+  return B200DET_OK;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- device helpers ---------------------------------------------------------------------
+// sigmoid as torch computes it: 1 / (1 + exp(-x)), IEEE division, full-precision expf.
+__device__ __forceinline__ float sigmoid_f32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// streaming (read-once) loads that do not allocate in L1
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+  float4 r;
+  asm("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg_stream_f1(const float* p) {
+  float r;
+  asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+// streaming (write-once) stores
+__device__ __forceinline__ void stg_stream_f4(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_stream_f1(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void stg_stream_s64(long long* p, long long v) {
+  asm volatile("st.global.cs.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// level of a level-major point index / of a tile index (branch-free over the small table)
+__device__ __forceinline__ int level_of_point(const LevelTable& t, int p) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < B200DET_MAX_LEVELS; ++i) l += (i < t.n_levels && p >= t.point_off[i]) ? 1 : 0;
+  return l;
+}
+__device__ __forceinline__ int level_of_tile(const LevelTable& t, int tile) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < B200DET_MAX_LEVELS; ++i) l += (i < t.n_levels && tile >= t.tile_off[i]) ? 1 : 0;
+  return l;
+}
+
+// order-preserving map float -> uint32 (larger float <=> larger key); -0 is folded onto +0
+__device__ __forceinline__ uint32_t order_key(float f) {
+  const uint32_t u = __float_as_uint(__fadd_rn(f, 0.0f));
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+
+}  // namespace b200det

@@ -1,0 +1,326 @@
+// K3 — batched NMS with the arithmetic of torchvision 0.26.0's CPU path (the op the reference
+// calls at model/modules/head.py:94), plus ClipBoxes (head.py:152-162) fused into the writer.
+//
+//   nms_prepare_kernel  (stand-alone entry only; K2 does this for the fused path)
+//       score >= thr compaction (order kept), stable descending sort, class-offset boxes.
+//   nms_mask_kernel     one CTA of 64 threads per 64x64 tile of the upper triangle: bit j of
+//       word (i, cb) says "box i suppresses box cb*64+j".  IoU in the reference's operation
+//       order with explicitly rounded fp32 intrinsics (no FMA contraction is possible):
+//         inter = max(0, min(x2)-max(x1)) * max(0, min(y2)-max(y1))
+//         iou   = inter / (area_i + area_j - inter),  suppressed iff (double)iou > thr.
+//   nms_scan_kernel     one CTA per image: greedy pass over the mask, 64 rows at a time staged
+//       into shared memory with cp.async (double-buffered); warp 0 resolves the 64x64 diagonal
+//       serially, all warps OR the kept rows into the removed-bitmap, and the kept boxes are
+//       written (clipped when asked) in keep order.
+// This stage is latency-bound (the greedy dependency chain), not bandwidth-bound.
+#include "block_utils.cuh"
+#include "nms.cuh"
+
+#include <math.h>
+
+namespace b200det {
+namespace {
+
+constexpr int kPrepThreads = 1024;
+constexpr int kScanThreads = 256;
+
+// ------------------------------------------------------------------------------------------
+// prepare (stand-alone batched_nms entry)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPrepThreads, 1)
+nms_prepare_kernel(const int n, const float* __restrict__ boxes, const float* __restrict__ scores,
+                   const long long* __restrict__ classes, const int32_t* __restrict__ in_count,
+                   const float thr, const CandSet set) {
+  extern __shared__ __align__(16) unsigned long long sortbuf[];   // [n2] keys, then [n] int source map
+  __shared__ int s_scan[33];
+  __shared__ float s_fmax[32];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x;
+  int n2 = next_pow2(n);
+  int* srcmap = reinterpret_cast<int*>(sortbuf + n2);
+  const int n_in = in_count ? min(max(in_count[b], 0), n) : n;
+  const float* sc = scores + (size_t)b * n;
+
+  // order-preserving threshold compaction: rank = index into the thresholded list (head.py:90-93)
+  int m = 0;
+  for (int base = 0; base < n_in; base += kPrepThreads) {
+    const int i = base + tid;
+    float s = 0.f;
+    const bool ok = (i < n_in) && ((s = sc[i]) >= thr);
+    int total;
+    const int rank = m + block_exclusive_scan(ok ? 1 : 0, s_scan, &total);
+    if (ok) {
+      sortbuf[rank] = ((unsigned long long)order_key(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)rank);
+      srcmap[rank] = i;
+    }
+    m += total;
+  }
+  if (m == 0) {
+    if (tid == 0) { set.count[b] = 0; set.mode[b] = 0; }
+    return;
+  }
+  n2 = next_pow2(m);
+  for (int i = m + tid; i < n2; i += kPrepThreads) sortbuf[i] = 0ull;
+  __syncthreads();
+  bitonic_sort_desc(sortbuf, n2);   // equal scores: lower rank first = stable descending
+
+  const size_t o0 = (size_t)b * set.cap;
+  float vmax = -CUDART_INF_F;
+  for (int i = tid; i < m; i += kPrepThreads) {
+    const unsigned long long e = sortbuf[i];
+    const int rank = (int)(0xffffffffu - (uint32_t)(e & 0xffffffffull));
+    const int src = srcmap[rank];
+    const float4 bx = reinterpret_cast<const float4*>(boxes)[(size_t)b * n + src];
+    set.score[o0 + i] = sc[src];
+    set.cls[o0 + i] = (int)classes[(size_t)b * n + src];
+    set.src[o0 + i] = rank;
+    reinterpret_cast<float4*>(set.box)[o0 + i] = bx;
+    vmax = fmaxf(vmax, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+  }
+  vmax = block_max(vmax, s_fmax);
+  nms_prepare_boxes(set, b, m, vmax, tid, kPrepThreads);
+  if (tid == 0) set.count[b] = m;
+}
+
+// ------------------------------------------------------------------------------------------
+// suppression mask
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNmsTile)
+nms_mask_kernel(const CandSet set, const int wcap, const float thr_up, const bool zero_suppresses,
+                unsigned long long* __restrict__ mask) {
+  const int cb = blockIdx.x, rb = blockIdx.y, b = blockIdx.z;
+  if (cb < rb) return;
+  const int n = set.count[b];
+  if (rb * kNmsTile >= n || cb * kNmsTile >= n) return;
+  const bool same_class_only = set.mode[b] == kModeVanilla;
+
+  __shared__ float4 cbox[kNmsTile];
+  __shared__ float carea[kNmsTile];
+  __shared__ int ccls[kNmsTile];
+  const int t = threadIdx.x;
+  const size_t o0 = (size_t)b * set.cap;
+  const int cj = cb * kNmsTile + t;
+  if (cj < n) {
+    const float4 v = reinterpret_cast<const float4*>(set.nms_box)[o0 + cj];
+    cbox[t] = v;
+    carea[t] = __fmul_rn(__fsub_rn(v.z, v.x), __fsub_rn(v.w, v.y));
+    ccls[t] = set.cls[o0 + cj];
+  }
+  __syncthreads();
+
+  const int i = rb * kNmsTile + t;
+  if (i >= n) return;
+  const float4 a = reinterpret_cast<const float4*>(set.nms_box)[o0 + i];
+  const float aarea = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const int acls = set.cls[o0 + i];
+  const int jend = min(kNmsTile, n - cb * kNmsTile);
+  unsigned long long bits = 0ull;
+  for (int j = (cb == rb) ? t + 1 : 0; j < jend; ++j) {
+    const float4 c = cbox[j];
+    const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, c.z), fmaxf(a.x, c.x)));
+    const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, c.w), fmaxf(a.y, c.y)));
+    bool sup;
+    if (!zero_suppresses && (w <= 0.f || h <= 0.f)) {
+      sup = false;                                   // inter = 0 -> iou is 0 or NaN, never > thr >= 0
+    } else {
+      const float inter = __fmul_rn(w, h);
+      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, carea[j]), inter));
+      sup = ovr >= thr_up;                           // == (double)ovr > thr, see launch_nms
+    }
+    if (same_class_only) sup = sup && (ccls[j] == acls);
+    if (sup) bits |= 1ull << j;
+  }
+  mask[(o0 + i) * wcap + cb] = bits;
+}
+
+// ------------------------------------------------------------------------------------------
+// greedy scan + output
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ float clip1(float v, float hi) { return fminf(fmaxf(v, 0.f), hi); }
+
+__global__ void __launch_bounds__(kScanThreads)
+nms_scan_kernel(const CandSet set, const int wcap, const unsigned long long* __restrict__ mask,
+                const int clip_h, const int clip_w, const NmsOut out) {
+  extern __shared__ __align__(16) unsigned long long sm[];   // [2][64*wcap] row chunks, [wcap] removed
+  __shared__ unsigned long long s_keep;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const int n = set.count[b];
+  const int W = (n + kNmsTile - 1) / kNmsTile;
+  const int Wr2 = ((W + 1) & ~1) / 2;                        // 16-byte units per row to stage
+  unsigned long long* removed = sm + 2 * kNmsTile * wcap;
+  const size_t o0 = (size_t)b * set.cap;
+  const size_t q0 = (size_t)b * out.stride;
+
+  for (int w = tid; w < wcap; w += kScanThreads) removed[w] = 0ull;
+
+  auto stage = [&](int rb) {
+    unsigned long long* dst = sm + (rb & 1) * kNmsTile * wcap;
+    const int rows = min(kNmsTile, n - rb * kNmsTile);
+    for (int e = tid; e < rows * Wr2; e += kScanThreads) {
+      const int r = e / Wr2, c = e - r * Wr2;
+      cp_async16(dst + r * wcap + 2 * c, mask + (o0 + rb * kNmsTile + r) * wcap + 2 * c);
+    }
+    cp_async_commit();
+  };
+
+  int total = 0;
+  if (W > 0) stage(0);
+  for (int rb = 0; rb < W; ++rb) {
+    if (rb + 1 < W) {
+      stage(rb + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();                                         // chunk rb (and removed[]) visible
+    const unsigned long long* chunk = sm + (rb & 1) * kNmsTile * wcap;
+    const int rows = min(kNmsTile, n - rb * kNmsTile);
+    if (warp == 0) {
+      unsigned long long cur = removed[rb], keep = 0ull;
+#pragma unroll 16
+      for (int i = 0; i < kNmsTile; ++i) {
+        const unsigned long long d = chunk[i * wcap + rb];   // broadcast read, off the dependency chain
+        const bool alive = (i < rows) && !((cur >> i) & 1ull);
+        keep |= alive ? (1ull << i) : 0ull;
+        cur |= alive ? d : 0ull;
+      }
+      if (lane == 0) s_keep = keep;
+    }
+    __syncthreads();
+    const unsigned long long keep = s_keep;
+    // removed[w] |= OR of the kept rows, for the column blocks still ahead
+    for (int w = rb + 1 + lane; w < W; w += 32) {
+      unsigned long long acc = 0ull;
+      for (int i = warp; i < rows; i += kScanThreads / 32)
+        if ((keep >> i) & 1ull) acc |= chunk[i * wcap + w];
+      if (acc) atomicOr(&removed[w], acc);
+    }
+    // kept boxes of this block, in order
+    if (tid < kNmsTile && ((keep >> tid) & 1ull)) {
+      const int q = rb * kNmsTile + tid;
+      const int o = total + __popcll(keep & ((1ull << tid) - 1ull));
+      float4 bx = reinterpret_cast<const float4*>(set.box)[o0 + q];
+      if (clip_h > 0) {   // ClipBoxes: clamp_(min=0), then x <= w-1, y <= h-1   (head.py:156-162)
+        bx.x = clip1(bx.x, (float)(clip_w - 1));
+        bx.y = clip1(bx.y, (float)(clip_h - 1));
+        bx.z = clip1(bx.z, (float)(clip_w - 1));
+        bx.w = clip1(bx.w, (float)(clip_h - 1));
+      }
+      out.score[q0 + o] = set.score[o0 + q];
+      out.cls[q0 + o] = (long long)set.cls[o0 + q];
+      out.keep[q0 + o] = (long long)set.src[o0 + q];
+      reinterpret_cast<float4*>(out.box)[q0 + o] = bx;
+    }
+    total += __popcll(keep);
+    __syncthreads();                                         // removed[] complete; chunk buffer reusable
+  }
+  if (tid == 0) out.count[b] = total;
+}
+
+struct NmsWorkspace {
+  CandSet set;
+  unsigned long long* mask;
+  size_t bytes;
+};
+
+// carve the candidate set + mask out of a workspace (base may be null to size only)
+NmsWorkspace carve_nms(void* base, int batch, int cap) {
+  NmsWorkspace w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const size_t bc = (size_t)batch * cap;
+  w.set.score = reinterpret_cast<float*>(take(bc * 4));
+  w.set.cls = reinterpret_cast<int32_t*>(take(bc * 4));
+  w.set.box = reinterpret_cast<float*>(take(bc * 16));
+  w.set.src = reinterpret_cast<int32_t*>(take(bc * 4));
+  w.set.nms_box = reinterpret_cast<float*>(take(bc * 16));
+  w.set.count = reinterpret_cast<int32_t*>(take((size_t)batch * 4));
+  w.set.mode = reinterpret_cast<int32_t*>(take((size_t)batch * 4));
+  w.set.cap = cap;
+  w.mask = reinterpret_cast<unsigned long long*>(take(bc * nms_mask_words(cap) * 8));
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace
+
+size_t nms_set_workspace_bytes(int batch, int cap) { return carve_nms(nullptr, batch, cap).bytes; }
+
+void nms_set_carve(void* base, int batch, int cap, CandSet* set, unsigned long long** mask) {
+  NmsWorkspace w = carve_nms(base, batch, cap);
+  *set = w.set;
+  *mask = w.mask;
+}
+
+int launch_nms(const CandSet& set, int batch, double nms_thr, int clip_h, int clip_w,
+               unsigned long long* mask, const NmsOut& out, cudaStream_t stream) {
+  const int wcap = nms_mask_words(set.cap);
+  // smallest fp32 F with (double)F > thr: for a non-NaN fp32 iou, (double)iou > thr  <=>  iou >= F
+  float thr_up = (float)nms_thr;
+  if (!((double)thr_up > nms_thr)) thr_up = nextafterf(thr_up, INFINITY);
+  const bool zero_suppresses = !(nms_thr >= 0.0);
+  const int wblocks = (set.cap + kNmsTile - 1) / kNmsTile;
+  nms_mask_kernel<<<dim3(wblocks, wblocks, batch), kNmsTile, 0, stream>>>(set, wcap, thr_up, zero_suppresses, mask);
+  int rc = check_launch();
+  if (rc) return rc;
+  const size_t smem = ((size_t)2 * kNmsTile * wcap + wcap) * sizeof(unsigned long long);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
+  }
+  nms_scan_kernel<<<batch, kScanThreads, smem, stream>>>(set, wcap, mask, clip_h, clip_w, out);
+  return check_launch();
+}
+
+}  // namespace b200det
+
+extern "C" size_t b200det_nms_workspace_bytes(int batch, int n) {
+  if (batch <= 0 || n <= 0 || n > B200DET_MAX_BOX) return 0;
+  return b200det::nms_set_workspace_bytes(batch, n);
+}
+
+extern "C" int b200det_batched_nms(int batch, int n, const float* boxes, const float* scores,
+                                   const int64_t* classes, const int32_t* in_count, float score_thr,
+                                   double nms_thr, int clip_h, int clip_w, void* workspace,
+                                   size_t workspace_bytes, float* out_score, int64_t* out_cls, float* out_box,
+                                   int64_t* out_keep, int32_t* out_count, void* stream) {
+  using namespace b200det;
+  if (batch <= 0 || batch > 65535 || n <= 0 || !boxes || !scores || !classes || !workspace || !out_score ||
+      !out_cls || !out_box || !out_keep || !out_count)
+    return B200DET_ERR_ARG;
+  if (n > B200DET_MAX_BOX) return B200DET_ERR_UNSUPPORTED;
+  if (!aligned16(boxes) || !aligned16(out_box) || !aligned16(workspace)) return B200DET_ERR_ARG;
+  if (workspace_bytes < nms_set_workspace_bytes(batch, n)) return B200DET_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CandSet set;
+  unsigned long long* mask;
+  nms_set_carve(workspace, batch, n, &set, &mask);
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  const size_t smem = (size_t)n2 * 8 + (size_t)n * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(nms_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
+  }
+  nms_prepare_kernel<<<batch, kPrepThreads, smem, st>>>(n, boxes, scores, reinterpret_cast<const long long*>(classes),
+                                                       in_count, score_thr, set);
+  int rc = check_launch();
+  if (rc) return rc;
+  NmsOut out{out_score, reinterpret_cast<long long*>(out_cls), out_box, reinterpret_cast<long long*>(out_keep),
+             out_count, n};
+  return launch_nms(set, batch, nms_thr, clip_h, clip_w, mask, out, st);
+}

@@ -1,0 +1,120 @@
+// K1 — per-point detection score straight from the NCHW head outputs.
+//
+// Replaces reshape_cat_out + sigmoid + max + sqrt of FCOSHead.forward (model/modules/head.py:8-26,
+// 53-64) without the NHWC copy the reference makes: a CTA owns 512 consecutive positions of one
+// level of one image and walks the C class planes, which are contiguous along hw, so every warp
+// load is a full 512-byte run.  sigmoid is monotone, so max_c sigmoid(x_c) = sigmoid(max_c x_c):
+// only the running max of the logits is kept (strict '>' in ascending class order = torch.max's
+// first-index rule) and ONE sigmoid per point is evaluated.  HBM-bound: (C+1)*4 bytes read and
+// 6 bytes written per point.
+#include "common.cuh"
+
+namespace b200det {
+namespace {
+
+constexpr int kUnroll = 8;   // independent 16-byte loads in flight per thread
+
+__device__ __forceinline__ void upd(float& best, int& arg, float v, int c) {
+  if (v > best) {
+    best = v;
+    arg = c;
+  }
+}
+
+__global__ void __launch_bounds__(kTileThreads)
+score_points_kernel(const LevelTable lt, const int C, float* __restrict__ score, int16_t* __restrict__ cls0) {
+  const int b = blockIdx.y;
+  const int l = level_of_tile(lt, blockIdx.x);
+  const int hw = lt.hw[l];
+  const int t0 = (blockIdx.x - lt.tile_off[l]) * kTile;
+  const float* __restrict__ cls = lt.cls[l] + (size_t)b * C * hw;
+  const float* __restrict__ cnt = lt.cnt[l] + (size_t)b * hw;
+  const size_t out0 = (size_t)b * lt.num_points + lt.point_off[l];
+
+  float best[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+  int arg[4] = {0, 0, 0, 0};
+  int pos[4];
+  float cn[4];
+
+  if (lt.vec_ok[l]) {
+    const int p0 = t0 + threadIdx.x * 4;
+    if (p0 >= hw) return;                    // hw % 4 == 0: a 4-group is all in or all out
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pos[q] = p0 + q;
+    const float* p = cls + p0;
+    int c = 0;
+    for (; c + kUnroll <= C; c += kUnroll) {
+      float4 v[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) v[u] = ldg_stream_f4(p + (size_t)(c + u) * hw);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        upd(best[0], arg[0], v[u].x, c + u);
+        upd(best[1], arg[1], v[u].y, c + u);
+        upd(best[2], arg[2], v[u].z, c + u);
+        upd(best[3], arg[3], v[u].w, c + u);
+      }
+    }
+    for (; c < C; ++c) {
+      const float4 v = ldg_stream_f4(p + (size_t)c * hw);
+      upd(best[0], arg[0], v.x, c);
+      upd(best[1], arg[1], v.y, c);
+      upd(best[2], arg[2], v.z, c);
+      upd(best[3], arg[3], v.w, c);
+    }
+    const float4 cv = ldg_stream_f4(cnt + p0);
+    cn[0] = cv.x; cn[1] = cv.y; cn[2] = cv.z; cn[3] = cv.w;
+  } else {
+    // planes not 16-byte aligned (e.g. 13x21 = 273): coalesced scalar loads, 4 strided points
+    bool in[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      pos[q] = t0 + threadIdx.x + q * kTileThreads;
+      in[q] = pos[q] < hw;
+    }
+    if (!in[0]) return;
+    for (int c = 0; c < C; ++c) {
+      const float* p = cls + (size_t)c * hw;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (in[q]) upd(best[q], arg[q], ldg_stream_f1(p + pos[q]), c);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      cn[q] = in[q] ? ldg_stream_f1(cnt + pos[q]) : 0.f;
+      if (!in[q]) pos[q] = -1;
+    }
+  }
+
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (pos[q] < 0) continue;
+    // head.py:57-63: sqrt(max_c sigmoid(cls) * sigmoid(cnt)), one rounding per operation
+    const float s = __fsqrt_rn(__fmul_rn(sigmoid_f32(best[q]), sigmoid_f32(cn[q])));
+    score[out0 + pos[q]] = s;
+    cls0[out0 + pos[q]] = (int16_t)arg[q];
+  }
+}
+
+}  // namespace
+
+int launch_score_points(const LevelTable& lt, int batch, int num_classes, float* score, int16_t* cls0,
+                        cudaStream_t stream) {
+  const dim3 grid(lt.tile_off[lt.n_levels], batch);
+  score_points_kernel<<<grid, kTileThreads, 0, stream>>>(lt, num_classes, score, cls0);
+  return check_launch();
+}
+
+}  // namespace b200det
+
+extern "C" int b200det_score_points(const b200det_level* levels, int n_levels, int batch, int num_classes,
+                                    float* score, int16_t* cls0, void* stream) {
+  using namespace b200det;
+  LevelTable lt;
+  if (!make_level_table(levels, n_levels, &lt) || batch <= 0 || batch > 65535 || num_classes <= 0 ||
+      num_classes > 32767 || !score || !cls0)
+    return B200DET_ERR_ARG;
+  for (int l = 0; l < n_levels; ++l)
+    if (!levels[l].cls || !levels[l].cnt) return B200DET_ERR_ARG;
+  return launch_score_points(lt, batch, num_classes, score, cls0, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,201 @@
+// K2 — per-image global top-k over all levels, sorted, with box decode.
+//
+// Replaces torch.topk + the per-image gathers of FCOSHead.forward (model/modules/head.py:66-80)
+// and the score threshold of post_process (head.py:90).  One CTA of 1024 threads per image:
+//   1. the image's P scores are read once (coalesced) into registers as order-preserving keys,
+//      sub-threshold points become key 0 (threshold-then-top-k selects the same set as the
+//      reference's top-k-then-threshold);
+//   2. the k-th largest key is found by a bitwise search over the key bits below the common
+//      prefix of min/max, one block-wide count per bit, stopping as soon as a count equals k;
+//      ties on the k-th key are broken by the lowest point index (a second bitwise search);
+//   3. the selected (key, ~index) pairs are bitonic-sorted in shared memory: score descending,
+//      point index ascending on equal scores (torch.topk leaves tie order unspecified);
+//   4. each selected point is decoded: box = (x - l, y - t, x + r, y + b) with
+//      (x, y) = (j*s + s/2, i*s + s/2) computed from the index (head.py:29-38, utills.py:58-73),
+//      class = argmax + 1, and — for K3 — the batched_nms coordinate-trick boxes are prepared.
+// The working set (4 bytes per point) is L2-resident right after K1; this kernel is latency-bound.
+#include "block_utils.cuh"
+#include "nms.cuh"
+
+namespace b200det {
+namespace {
+
+constexpr int kSelThreads = 1024;
+constexpr int kSelItems = 24;            // register-resident keys per thread: P <= 24576
+
+__device__ __forceinline__ uint32_t load_key(const float* sc, int i, float thr) {
+  const float s = sc[i];
+  return (s >= thr) ? order_key(s) : 0u;
+}
+
+// Sum over the CTA with ONE barrier per call (double-buffered scratch, 2 x 32 ints).
+__device__ __forceinline__ int block_sum(int v, int* buf, int& phase) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = __reduce_add_sync(0xffffffffu, v);
+  int* bp = buf + (phase & 1) * 32;
+  if (lane == 0) bp[warp] = v;
+  __syncthreads();
+  int r = (lane < (kSelThreads >> 5)) ? bp[lane] : 0;
+  r = __reduce_add_sync(0xffffffffu, r);
+  ++phase;
+  return r;
+}
+
+#define FOR_KEYS(BODY)                                                  \
+  if constexpr (REG) {                                                  \
+    _Pragma("unroll") for (int j_ = 0; j_ < kSelItems; ++j_) {          \
+      const uint32_t kx = key[j_];                                      \
+      const int ix = tid + j_ * kSelThreads;                            \
+      BODY                                                              \
+    }                                                                   \
+  } else {                                                              \
+    for (int ix = tid; ix < P; ix += kSelThreads) {                     \
+      const uint32_t kx = load_key(sc, ix, thr);                        \
+      BODY                                                              \
+    }                                                                   \
+  }
+
+template <bool REG>
+__global__ void __launch_bounds__(kSelThreads, 1)
+select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const int16_t* __restrict__ cls0,
+                   const float thr, const int max_box, const CandSet out, int32_t* __restrict__ cand_point) {
+  extern __shared__ __align__(16) unsigned long long sortbuf[];
+  __shared__ int s_red[64];
+  __shared__ int s_scan[33];
+  __shared__ uint32_t s_mm[64];
+  __shared__ float s_fmax[32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const int P = lt.num_points;
+  const float* sc = score + (size_t)b * P;
+  int phase = 0;
+
+  uint32_t key[REG ? kSelItems : 1];
+  int nv = 0;
+  uint32_t kmin = 0xffffffffu, kmax = 0u;
+  if (REG) {
+#pragma unroll
+    for (int j = 0; j < kSelItems; ++j) {
+      const int i = tid + j * kSelThreads;
+      key[j] = (i < P) ? load_key(sc, i, thr) : 0u;
+    }
+  }
+  FOR_KEYS(if (kx) { ++nv; kmin = min(kmin, kx); kmax = max(kmax, kx); })
+
+  // block-wide n_valid / min / max
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  if (lane == 0) { s_mm[warp] = kmin; s_mm[32 + warp] = kmax; }
+  const int n_valid = block_sum(nv, s_red, phase);   // barrier inside also publishes s_mm
+  kmin = __reduce_min_sync(0xffffffffu, s_mm[lane]);
+  kmax = __reduce_max_sync(0xffffffffu, s_mm[32 + lane]);
+
+  const int kk = min(min(max_box, P), n_valid);
+  if (kk == 0) {
+    if (tid == 0) { out.count[b] = 0; out.mode[b] = 0; }
+    return;
+  }
+
+  // ---- k-th largest key -----------------------------------------------------------------
+  uint32_t T = kmin;          // count(key >= kmin) = n_valid
+  int cntT = n_valid;
+  if (n_valid > kk) {
+    const uint32_t diff = kmin ^ kmax;              // non-zero here unless all keys are equal
+    const int top = diff ? 31 - __clz(diff) : -1;
+    T = (top >= 0) ? (kmax & ~((2u << top) - 1u)) : kmax;
+    for (int bit = top; bit >= 0; --bit) {
+      const uint32_t cand = T | (1u << bit);
+      int c = 0;
+      FOR_KEYS(c += (kx >= cand) ? 1 : 0;)
+      c = block_sum(c, s_red, phase);
+      if (c >= kk) {
+        T = cand;
+        cntT = c;
+        if (c == kk) break;
+      }
+    }
+  }
+  // cntT = count(key >= T) >= kk.  If larger, T is exactly the k-th key and ties straddle it.
+  int idx_lim = 0x7fffffff;
+  if (cntT > kk) {
+    int c = 0;
+    FOR_KEYS(c += (kx > T) ? 1 : 0;)
+    const int c_gt = block_sum(c, s_red, phase);
+    const int r = kk - c_gt;                        // how many == T to take, lowest index first
+    int L = 0;                                      // largest L with count(key==T && idx<L) <= r
+    for (int bit = 31 - __clz(P); bit >= 0; --bit) {
+      const int cand = L | (1 << bit);
+      int e = 0;
+      FOR_KEYS(e += (kx == T && ix < cand) ? 1 : 0;)
+      e = block_sum(e, s_red, phase);
+      if (e <= r) L = cand;
+    }
+    idx_lim = L;
+  }
+
+  // ---- compaction (order irrelevant: sorted next) ---------------------------------------
+  int mine = 0;
+  FOR_KEYS(mine += (kx > T || (kx == T && ix < idx_lim)) ? 1 : 0;)
+  int total;
+  int at = block_exclusive_scan(mine, s_scan, &total);    // total == kk
+  FOR_KEYS(if (kx > T || (kx == T && ix < idx_lim)) {
+    sortbuf[at++] = ((unsigned long long)kx << 32) | (unsigned long long)(0xffffffffu - (uint32_t)ix);
+  })
+  const int n2 = next_pow2(kk);
+  for (int i = kk + tid; i < n2; i += kSelThreads) sortbuf[i] = 0ull;
+  __syncthreads();
+  bitonic_sort_desc(sortbuf, n2);
+
+  // ---- gather + decode + NMS preparation ------------------------------------------------
+  const size_t o0 = (size_t)b * out.cap;
+  float vmax = -CUDART_INF_F;
+  for (int i = tid; i < kk; i += kSelThreads) {
+    const unsigned long long e = sortbuf[i];
+    const int p = (int)(0xffffffffu - (uint32_t)(e & 0xffffffffull));
+    const int l = level_of_point(lt, p);
+    const int pos = p - lt.point_off[l];
+    const int hw = lt.hw[l], w = lt.w[l], s = lt.stride[l];
+    const float x = (float)((pos % w) * s + s / 2);
+    const float y = (float)((pos / w) * s + s / 2);
+    const float* rg = lt.reg[l] + (size_t)b * 4 * hw + pos;
+    float4 bx;
+    bx.x = __fsub_rn(x, rg[0]);
+    bx.y = __fsub_rn(y, rg[hw]);
+    bx.z = __fadd_rn(x, rg[2 * hw]);
+    bx.w = __fadd_rn(y, rg[3 * hw]);
+    out.score[o0 + i] = key_to_float((uint32_t)(e >> 32));
+    out.cls[o0 + i] = (int)cls0[(size_t)b * P + p] + 1;
+    out.src[o0 + i] = i;
+    if (cand_point) cand_point[o0 + i] = p;
+    reinterpret_cast<float4*>(out.box)[o0 + i] = bx;
+    vmax = fmaxf(vmax, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+  }
+  if (out.nms_box) {
+    vmax = block_max(vmax, s_fmax);
+    nms_prepare_boxes(out, b, kk, vmax, tid, kSelThreads);
+  }
+  if (tid == 0) out.count[b] = kk;
+}
+
+}  // namespace
+
+int launch_select_topk(const LevelTable& lt, int batch, const float* score, const int16_t* cls0, float thr,
+                       int max_box, const CandSet& out, int32_t* cand_point, cudaStream_t stream) {
+  const int k = max_box < lt.num_points ? max_box : lt.num_points;
+  int n2 = 1;
+  while (n2 < k) n2 <<= 1;
+  const size_t smem = (size_t)n2 * sizeof(unsigned long long);
+  if (lt.num_points <= kSelItems * kSelThreads) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(select_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    select_topk_kernel<true><<<batch, kSelThreads, smem, stream>>>(lt, score, cls0, thr, max_box, out, cand_point);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(select_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    select_topk_kernel<false><<<batch, kSelThreads, smem, stream>>>(lt, score, cls0, thr, max_box, out, cand_point);
+  }
+  return check_launch();
+}
+
+}  // namespace b200det

@@ -1,0 +1,151 @@
+"""Drop-in mirrors of the reference's ``model/loss.py``, backed by the CUDA library.
+
+``FCOSLoss`` (loss.py:196-215) and the free functions ``compute_cls_loss`` (loss.py:6-26),
+``compute_cnt_loss`` (loss.py:29-57), ``compute_reg_loss`` (loss.py:116-139), ``iou_loss``
+(loss.py:142-152), ``giou_loss`` (loss.py:155-177) and ``focal_loss_from_logits``
+(loss.py:180-193) keep their signatures, return shapes and error behaviour.  Each is one fused
+forward kernel and one fused backward kernel that read / write the per-level NCHW maps in place;
+autograd sees them through ``torch.autograd.Function``.  Nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+Tensor = torch.Tensor
+_MODES = {"iou": 0, "giou": 1}
+
+
+def _mask_source(mask: Tensor) -> Tensor:
+    """bool [B,P] -> float [B,P] with positives > -1 (what the kernels test, loss.py:205)."""
+    return torch.where(mask, 0.0, -1.0).to(torch.float32)
+
+
+class _BoxLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mask_src: Tensor, reg_t: Tensor, mode: int, *reg: Tensor):
+        loss, npos = ops.box_loss_fwd(reg, mask_src, reg_t, mode)
+        ctx.save_for_backward(mask_src, reg_t, npos, *reg)
+        ctx.mode = mode
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss: Tensor):
+        mask_src, reg_t, npos, *reg = ctx.saved_tensors
+        grads = ops.box_loss_bwd(reg, mask_src, reg_t, ctx.mode, grad_loss, npos)
+        return (None, None, None, *[g.to(r.dtype) for g, r in zip(grads, reg)])
+
+
+class _CntLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mask_src: Tensor, cnt_t: Tensor, *cnt: Tensor):
+        loss, npos = ops.cnt_loss_fwd(cnt, mask_src, cnt_t)
+        ctx.save_for_backward(mask_src, cnt_t, npos, *cnt)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss: Tensor):
+        mask_src, cnt_t, npos, *cnt = ctx.saved_tensors
+        grads = ops.cnt_loss_bwd(cnt, mask_src, cnt_t, grad_loss, npos)
+        return (None, None, *[g.to(c.dtype) for g, c in zip(grads, cnt)])
+
+
+class _ClsLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mask_src: Tensor, cls_t: Tensor, *cls: Tensor):
+        loss, npos = ops.cls_loss_fwd(cls, mask_src, cls_t)
+        ctx.save_for_backward(cls_t, npos, *cls)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss: Tensor):
+        cls_t, npos, *cls = ctx.saved_tensors
+        grads = ops.cls_loss_bwd(cls, cls_t, grad_loss, npos)
+        return (None, None, *[g.to(c.dtype) for g, c in zip(grads, cls)])
+
+
+def _check_points(preds: Sequence[Tensor], target: Tensor) -> None:
+    p = sum(int(t.shape[2]) * int(t.shape[3]) for t in preds)
+    assert p == target.shape[1] and preds[0].shape[0] == target.shape[0], \
+        f"predictions cover [{preds[0].shape[0]}, {p}] points, target {tuple(target.shape[:2])}"
+
+
+def compute_cls_loss(preds: List[Tensor], target: Tensor, mask: Tensor, _mask_src: Tensor | None = None) -> Tensor:
+    """Focal loss over all points / clamp(num_pos, 1) -> [B] (loss.py:6-26)."""
+    _check_points(preds, target)                                   # loss.py:18
+    return _ClsLoss.apply(_mask_source(mask) if _mask_src is None else _mask_src, target, *preds)
+
+
+def compute_cnt_loss(preds: List[Tensor], target: Tensor, mask: Tensor, _mask_src: Tensor | None = None) -> Tensor:
+    """BCE-with-logits over positives / clamp(num_pos, 1) -> [B] (loss.py:29-57)."""
+    _check_points(preds, target)                                   # loss.py:41
+    assert target.shape[-1] == 1 and preds[0].shape[1] == 1
+    return _CntLoss.apply(_mask_source(mask) if _mask_src is None else _mask_src, target, *preds)
+
+
+def compute_reg_loss(preds: List[Tensor], target: Tensor, mask: Tensor, mode: str = "iou",
+                     _mask_src: Tensor | None = None) -> Tensor:
+    """IoU / GIoU loss over positives / clamp(num_pos, 1) -> [B] (loss.py:116-139)."""
+    _check_points(preds, target)                                   # loss.py:127
+    assert target.shape[-1] == 4 and preds[0].shape[1] == 4
+    if mode not in _MODES:
+        raise NotImplementedError("reg loss only implemented ['iou','giou']")   # loss.py:137-138
+    return _BoxLoss.apply(_mask_source(mask) if _mask_src is None else _mask_src, target, _MODES[mode], *preds)
+
+
+def _pairwise(preds: Tensor, targets: Tensor, mode: int) -> Tensor:
+    # [n,4] pairs as a single one-image, one-level problem: preds -> [1,4,n,1] map, every row positive
+    n = preds.shape[0]
+    if n == 0:
+        return preds.sum() * 0.0
+    level = preds.t().reshape(1, 4, n, 1)
+    mask_src = torch.zeros((1, n), dtype=torch.float32, device=preds.device)
+    loss = _BoxLoss.apply(mask_src, targets.reshape(1, n, 4), mode, level)
+    return (loss * float(n)).reshape(())          # kernel divides by num_pos = n; the reference returns the sum
+
+
+def iou_loss(preds: Tensor, targets: Tensor) -> Tensor:
+    """-log(clamp(iou, 1e-6)) summed over [n,4] ltrb pairs (loss.py:142-152)."""
+    return _pairwise(preds, targets, 0)
+
+
+def giou_loss(preds: Tensor, targets: Tensor) -> Tensor:
+    """(1 - giou) summed over [n,4] ltrb pairs (loss.py:155-177)."""
+    return _pairwise(preds, targets, 1)
+
+
+def focal_loss_from_logits(preds: Tensor, targets: Tensor, gamma: float = 2.0, alpha: float = 0.25) -> Tensor:
+    """Summed focal loss of logits [P,C] against one-hot targets [P,C] (loss.py:180-193)."""
+    if gamma != 2.0 or alpha != 0.25:
+        raise NotImplementedError("the CUDA focal loss is specialised for gamma=2.0, alpha=0.25 (the reference's call)")
+    p, c = preds.shape
+    hot = targets > 0.5
+    assert bool((hot.sum(dim=1) <= 1).all()), "targets must be one-hot rows (or all zero)"
+    cls_t = torch.where(hot.any(dim=1), hot.float().argmax(dim=1) + 1, 0).reshape(1, p, 1)
+    level = preds.t().reshape(1, c, p, 1)
+    mask_src = torch.full((1, p), -1.0, dtype=torch.float32, device=preds.device)   # num_pos clamps to 1
+    return _ClsLoss.apply(mask_src, cls_t, level).reshape(())
+
+
+class FCOSLoss(nn.Module):
+    """(cls_loss, cnt_loss, reg_loss, total_loss) as 0-dim tensors (loss.py:196-215)."""
+
+    def __init__(self, mode: str = "giou"):
+        super().__init__()
+        self.mode = mode
+
+    def forward(self, x):
+        pred, target = x
+        cls_logit, cnt_logit, reg_logit = pred
+        cls_target, cnt_target, reg_target = target
+        mask_pos = None                    # loss.py:205: cnt_target > -1; the kernels test cnt_target directly
+        src = cnt_target
+        cls_loss = compute_cls_loss(cls_logit, cls_target, mask_pos, _mask_src=src).mean()
+        cnt_loss = compute_cnt_loss(cnt_logit, cnt_target, mask_pos, _mask_src=src).mean()
+        reg_loss = compute_reg_loss(reg_logit, reg_target, mask_pos, self.mode, _mask_src=src).mean()
+        total_loss = cls_loss + cnt_loss + reg_loss
+        return cls_loss, cnt_loss, reg_loss, total_loss

@@ -1,0 +1,395 @@
+"""torch.library ops of the ``b200det`` namespace — thin wrappers over the C ABI.
+
+Every op takes CUDA tensors, allocates its outputs/workspace with torch (the library never
+allocates), launches on the current CUDA stream and returns without synchronising.  There is
+no CPU implementation and no other backend: a non-CUDA tensor raises.
+
+Shapes use the reference's conventions (``model/modules/head.py``, ``model/loss.py``):
+level lists are NCHW fp32 maps, points are numbered level-major / row-major (the order
+``reshape_cat_out`` produces), ``zip(levels, strides)`` truncation included (head.py:20).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+Tensor = torch.Tensor
+launch_count = 0          # kernels launched through this module (bench.py reports it)
+
+# kernels per C entry point (see csrc/*.cu)
+_LAUNCHES = {"postprocess": 4, "batched_nms": 3, "score_points": 1, "select_topk": 1, "clip_boxes": 1,
+             "assign_targets": 1, "box_loss_fwd": 1, "box_loss_bwd": 1, "cnt_loss_fwd": 1, "cnt_loss_bwd": 1,
+             "cls_loss_fwd": 2, "cls_loss_bwd": 1}
+
+
+def _count(name: str) -> None:
+    global launch_count
+    launch_count += _LAUNCHES[name]
+
+
+def _stream(t: Tensor) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _need_cuda(t: Tensor, what: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.B200DetError(f"{what} must be a CUDA tensor: b200det has no CPU path "
+                                f"(got {getattr(t, 'device', type(t))})")
+
+
+def _f32c(t: Tensor, what: str) -> Tensor:
+    _need_cuda(t, what)
+    if t.dtype != torch.float32:
+        t = t.float()         # AMP fp16/bf16 head outputs are evaluated in fp32
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _levels(cls: Sequence[Tensor] | None, cnt: Sequence[Tensor] | None, reg: Sequence[Tensor] | None,
+            strides: Sequence[int]):
+    """zip()-truncated level table.  Returns (ctypes array, kept tensors, P, batch, n_levels)."""
+    lists = [l for l in (cls, cnt, reg) if l is not None]
+    n = min([len(strides)] + [len(l) for l in lists])
+    if n == 0:
+        raise _lib.B200DetError("no levels")
+    keep: List[Tensor] = []
+    entries = []
+    batch = None
+    p_total = 0
+    for i in range(n):
+        ptrs = []
+        hw = None
+        for lst, ch in ((cls, None), (cnt, 1), (reg, 4)):
+            if lst is None:
+                ptrs.append(0)
+                continue
+            t = _f32c(lst[i], "level map")
+            if t.dim() != 4 or (ch is not None and t.shape[1] != ch):
+                raise _lib.B200DetError(f"level {i}: expected [B,{ch or 'C'},h,w], got {tuple(t.shape)}")
+            if hw is None:
+                hw = (t.shape[2], t.shape[3])
+            elif hw != (t.shape[2], t.shape[3]):
+                raise _lib.B200DetError(f"level {i}: cls/cnt/reg spatial sizes differ")
+            if batch is None:
+                batch = t.shape[0]
+            elif batch != t.shape[0]:
+                raise _lib.B200DetError("batch sizes differ between level maps")
+            keep.append(t)
+            ptrs.append(t.data_ptr())
+        entries.append((ptrs[0], ptrs[1], ptrs[2], hw[0], hw[1], int(strides[i])))
+        p_total += hw[0] * hw[1]
+    return _lib.make_levels(entries), keep, p_total, batch, n
+
+
+# --------------------------------------------------------------------------------------------
+# inference
+# --------------------------------------------------------------------------------------------
+def postprocess(cls: Sequence[Tensor], cnt: Sequence[Tensor], reg: Sequence[Tensor], strides: Sequence[int],
+                score_thr: float, nms_thr: float, max_box: int, clip_hw: Tuple[int, int] | None = None):
+    """FCOSHead.forward (+ ClipBoxes) for any batch size, padded outputs.
+
+    Returns scores [B,K] f32, classes [B,K] i64 (1-based), boxes [B,K,4] f32, keep [B,K] i64,
+    counts [B] i32 with K = min(max_box, P); rows beyond counts[b] are unspecified.
+    """
+    lib = _lib.load()
+    lv, keep_alive, p_total, batch, n = _levels(cls, cnt, reg, strides)
+    dev = keep_alive[0].device
+    k = min(int(max_box), p_total)
+    if k > _lib.MAX_BOX:
+        raise _lib.B200DetError(f"max_detection_box {k} > {_lib.MAX_BOX}")
+    ncls = keep_alive[0].shape[1]
+    ws_bytes = lib.b200det_postprocess_workspace_bytes(batch, p_total, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    scores = torch.empty((batch, k), dtype=torch.float32, device=dev)
+    classes = torch.empty((batch, k), dtype=torch.int64, device=dev)
+    boxes = torch.empty((batch, k, 4), dtype=torch.float32, device=dev)
+    keep = torch.empty((batch, k), dtype=torch.int64, device=dev)
+    counts = torch.empty((batch,), dtype=torch.int32, device=dev)
+    ch, cw = (int(clip_hw[0]), int(clip_hw[1])) if clip_hw else (0, 0)
+    with torch.cuda.device(dev):
+        rc = lib.b200det_postprocess(lv, n, batch, ncls, float(score_thr), float(nms_thr), k, ch, cw,
+                                     ws.data_ptr(), ws_bytes, scores.data_ptr(), classes.data_ptr(),
+                                     boxes.data_ptr(), keep.data_ptr(), counts.data_ptr(), _stream(ws))
+    _lib.check(rc, "b200det_postprocess")
+    _count("postprocess")
+    return scores, classes, boxes, keep, counts
+
+
+def score_points(cls: Sequence[Tensor], cnt: Sequence[Tensor], strides: Sequence[int]):
+    """K1 alone: score [B,P] f32, class argmax [B,P] i16 (0-based)."""
+    lib = _lib.load()
+    lv, keep_alive, p_total, batch, n = _levels(cls, cnt, None, strides)
+    dev = keep_alive[0].device
+    score = torch.empty((batch, p_total), dtype=torch.float32, device=dev)
+    cls0 = torch.empty((batch, p_total), dtype=torch.int16, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.b200det_score_points(lv, n, batch, keep_alive[0].shape[1], score.data_ptr(), cls0.data_ptr(),
+                                      _stream(score))
+    _lib.check(rc, "b200det_score_points")
+    _count("score_points")
+    return score, cls0
+
+
+def select_topk(reg: Sequence[Tensor], strides: Sequence[int], score: Tensor, cls0: Tensor, score_thr: float,
+                max_box: int):
+    """K2 alone: (scores [B,K], classes [B,K] i32, boxes [B,K,4], points [B,K] i32, counts [B] i32)."""
+    lib = _lib.load()
+    lv, keep_alive, p_total, batch, n = _levels(None, None, reg, strides)
+    dev = score.device
+    k = min(int(max_box), p_total)
+    assert score.shape == (batch, p_total) and score.is_contiguous() and cls0.is_contiguous()
+    s = torch.empty((batch, k), dtype=torch.float32, device=dev)
+    c = torch.empty((batch, k), dtype=torch.int32, device=dev)
+    b = torch.empty((batch, k, 4), dtype=torch.float32, device=dev)
+    p = torch.empty((batch, k), dtype=torch.int32, device=dev)
+    cnt = torch.empty((batch,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.b200det_select_topk(lv, n, batch, score.data_ptr(), cls0.data_ptr(), float(score_thr), k,
+                                     s.data_ptr(), c.data_ptr(), b.data_ptr(), p.data_ptr(), cnt.data_ptr(),
+                                     _stream(score))
+    _lib.check(rc, "b200det_select_topk")
+    _count("select_topk")
+    return s, c, b, p, cnt
+
+
+def batched_nms(boxes: Tensor, scores: Tensor, classes: Tensor, score_thr: float, nms_thr: float,
+                in_count: Tensor | None = None, clip_hw: Tuple[int, int] | None = None):
+    """post_process (head.py:84-102) on [B,n] candidates: threshold -> torchvision-CPU-exact NMS.
+
+    Returns scores [B,n], classes [B,n] i64, boxes [B,n,4], keep [B,n] i64 (index into the image's
+    thresholded candidate list, as ``torchvision.ops.batched_nms`` returns), counts [B] i32.
+    """
+    lib = _lib.load()
+    _need_cuda(boxes, "boxes")
+    dev = boxes.device
+    boxes = _f32c(boxes, "boxes")
+    scores = _f32c(scores, "scores")
+    _need_cuda(classes, "classes")
+    classes = classes.to(torch.int64).contiguous()
+    batch, n = scores.shape
+    if boxes.shape != (batch, n, 4) or classes.shape != (batch, n):
+        raise _lib.B200DetError("batched_nms expects boxes [B,n,4], scores [B,n], classes [B,n]")
+    o_s = torch.empty((batch, n), dtype=torch.float32, device=dev)
+    o_c = torch.empty((batch, n), dtype=torch.int64, device=dev)
+    o_b = torch.empty((batch, n, 4), dtype=torch.float32, device=dev)
+    o_k = torch.empty((batch, n), dtype=torch.int64, device=dev)
+    counts = torch.zeros((batch,), dtype=torch.int32, device=dev)
+    if n == 0 or batch == 0:
+        return o_s, o_c, o_b, o_k, counts
+    if n > _lib.MAX_BOX:
+        raise _lib.B200DetError(f"{n} candidates per image > {_lib.MAX_BOX}")
+    if in_count is not None:
+        in_count = in_count.to(device=dev, dtype=torch.int32).contiguous()
+    ws_bytes = lib.b200det_nms_workspace_bytes(batch, n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ch, cw = (int(clip_hw[0]), int(clip_hw[1])) if clip_hw else (0, 0)
+    with torch.cuda.device(dev):
+        rc = lib.b200det_batched_nms(batch, n, boxes.data_ptr(), scores.data_ptr(), classes.data_ptr(),
+                                     in_count.data_ptr() if in_count is not None else None,
+                                     float(score_thr), float(nms_thr), ch, cw, ws.data_ptr(), ws_bytes,
+                                     o_s.data_ptr(), o_c.data_ptr(), o_b.data_ptr(), o_k.data_ptr(),
+                                     counts.data_ptr(), _stream(ws))
+    _lib.check(rc, "b200det_batched_nms")
+    _count("batched_nms")
+    return o_s, o_c, o_b, o_k, counts
+
+
+def clip_boxes_(boxes: Tensor, img_h: int, img_w: int) -> Tensor:
+    """ClipBoxes.forward: in-place, returns the same tensor (head.py:156-162)."""
+    lib = _lib.load()
+    _need_cuda(boxes, "boxes")
+    if boxes.numel() == 0:
+        return boxes
+    if boxes.shape[-1] != 4:
+        raise _lib.B200DetError("boxes must end in a dimension of 4")
+    work = boxes
+    direct = boxes.dtype == torch.float32 and boxes.is_contiguous() and boxes.data_ptr() % 16 == 0
+    if not direct:
+        work = boxes.float().contiguous()
+    with torch.cuda.device(boxes.device):
+        rc = lib.b200det_clip_boxes(work.data_ptr(), work.numel() // 4, int(img_h), int(img_w), _stream(work))
+    _lib.check(rc, "b200det_clip_boxes")
+    _count("clip_boxes")
+    if not direct:
+        boxes.copy_(work)
+    return boxes
+
+
+# --------------------------------------------------------------------------------------------
+# training targets
+# --------------------------------------------------------------------------------------------
+def assign_targets(level_hw: Sequence[Tuple[int, int]], strides: Sequence[int],
+                   limit_range: Sequence[Sequence[float]], gt_boxes: Tensor, labels: Tensor,
+                   sample_radius: float = 1.5, want_index: bool = False):
+    """FCOSGenTargets.forward: cls_t [B,P,1] i64, cnt_t [B,P,1] f32, reg_t [B,P,4] f32 (+ gt index [B,P] i32)."""
+    lib = _lib.load()
+    _need_cuda(gt_boxes, "gt_boxes")
+    _need_cuda(labels, "labels")
+    dev = gt_boxes.device
+    gt = _f32c(gt_boxes, "gt_boxes")
+    lab = labels.to(torch.int64).contiguous()
+    if gt.dim() != 3 or gt.shape[-1] != 4 or lab.shape != gt.shape[:2]:
+        raise _lib.B200DetError("expected gt_boxes [B,M,4] and labels [B,M]")
+    batch, m = lab.shape
+    n = len(level_hw)
+    assert len(strides) == n and len(limit_range) == n
+    p_total = sum(h * w for h, w in level_hw)
+    hw_arr = (C.c_int32 * (2 * n))(*[v for hw in level_hw for v in hw])
+    st_arr = (C.c_int32 * n)(*[int(s) for s in strides])
+    lo_arr = (C.c_float * n)(*[float(r[0]) for r in limit_range])
+    hi_arr = (C.c_float * n)(*[float(r[1]) for r in limit_range])
+    ra_arr = (C.c_float * n)(*[float(s * sample_radius) for s in strides])
+    cls_t = torch.empty((batch, p_total, 1), dtype=torch.int64, device=dev)
+    cnt_t = torch.empty((batch, p_total, 1), dtype=torch.float32, device=dev)
+    reg_t = torch.empty((batch, p_total, 4), dtype=torch.float32, device=dev)
+    idx = torch.empty((batch, p_total), dtype=torch.int32, device=dev) if want_index else None
+    with torch.cuda.device(dev):
+        rc = lib.b200det_assign_targets(hw_arr, st_arr, lo_arr, hi_arr, ra_arr, n, batch, m, gt.data_ptr(),
+                                        lab.data_ptr(), cls_t.data_ptr(), cnt_t.data_ptr(), reg_t.data_ptr(),
+                                        idx.data_ptr() if idx is not None else None, _stream(gt))
+    _lib.check(rc, "b200det_assign_targets")
+    _count("assign_targets")
+    return (cls_t, cnt_t, reg_t, idx) if want_index else (cls_t, cnt_t, reg_t)
+
+
+# --------------------------------------------------------------------------------------------
+# losses (forward / backward pairs; autograd glue lives in loss.py)
+# --------------------------------------------------------------------------------------------
+def _mask_src(mask_src: Tensor, batch: int, p_total: int) -> Tensor:
+    m = _f32c(mask_src, "mask source").reshape(batch, -1)
+    if m.shape[1] != p_total:
+        raise AssertionError(f"targets cover {m.shape[1]} points, predictions {p_total}")
+    return m
+
+
+def _grad_ptrs(grads: Sequence[Tensor]):
+    return (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+
+
+def box_loss_fwd(reg: Sequence[Tensor], mask_src: Tensor, reg_t: Tensor, mode: int):
+    lib = _lib.load()
+    lv, keep_alive, p_total, batch, n = _levels(None, None, reg, [1] * len(reg))
+    m = _mask_src(mask_src, batch, p_total)
+    t = _f32c(reg_t, "reg target").reshape(batch, p_total, 4)
+    loss = torch.empty((batch,), dtype=torch.float32, device=m.device)
+    npos = torch.empty_like(loss)
+    with torch.cuda.device(m.device):
+        rc = lib.b200det_box_loss_fwd(lv, n, batch, m.data_ptr(), t.data_ptr(), mode, loss.data_ptr(),
+                                      npos.data_ptr(), _stream(m))
+    _lib.check(rc, "b200det_box_loss_fwd")
+    _count("box_loss_fwd")
+    return loss, npos
+
+
+def box_loss_bwd(reg: Sequence[Tensor], mask_src: Tensor, reg_t: Tensor, mode: int, grad_loss: Tensor,
+                 npos: Tensor) -> List[Tensor]:
+    lib = _lib.load()
+    lv, keep_alive, p_total, batch, n = _levels(None, None, reg, [1] * len(reg))
+    m = _mask_src(mask_src, batch, p_total)
+    t = _f32c(reg_t, "reg target").reshape(batch, p_total, 4)
+    g = _f32c(grad_loss, "grad").reshape(batch)
+    grads = [torch.empty_like(x) for x in keep_alive]
+    with torch.cuda.device(m.device):
+        rc = lib.b200det_box_loss_bwd(lv, _grad_ptrs(grads), n, batch, m.data_ptr(), t.data_ptr(), mode,
+                                      g.data_ptr(), npos.data_ptr(), _stream(m))
+    _lib.check(rc, "b200det_box_loss_bwd")
+    _count("box_loss_bwd")
+    return grads
+
+
+def cnt_loss_fwd(cnt: Sequence[Tensor], mask_src: Tensor, cnt_t: Tensor):
+    lib = _lib.load()
+    lv, keep_alive, p_total, batch, n = _levels(None, cnt, None, [1] * len(cnt))
+    m = _mask_src(mask_src, batch, p_total)
+    t = _mask_src(cnt_t, batch, p_total)
+    loss = torch.empty((batch,), dtype=torch.float32, device=m.device)
+    npos = torch.empty_like(loss)
+    with torch.cuda.device(m.device):
+        rc = lib.b200det_cnt_loss_fwd(lv, n, batch, m.data_ptr(), t.data_ptr(), loss.data_ptr(), npos.data_ptr(),
+                                      _stream(m))
+    _lib.check(rc, "b200det_cnt_loss_fwd")
+    _count("cnt_loss_fwd")
+    return loss, npos
+
+
+def cnt_loss_bwd(cnt: Sequence[Tensor], mask_src: Tensor, cnt_t: Tensor, grad_loss: Tensor, npos: Tensor):
+    lib = _lib.load()
+    lv, keep_alive, p_total, batch, n = _levels(None, cnt, None, [1] * len(cnt))
+    m = _mask_src(mask_src, batch, p_total)
+    t = _mask_src(cnt_t, batch, p_total)
+    g = _f32c(grad_loss, "grad").reshape(batch)
+    grads = [torch.empty_like(x) for x in keep_alive]
+    with torch.cuda.device(m.device):
+        rc = lib.b200det_cnt_loss_bwd(lv, _grad_ptrs(grads), n, batch, m.data_ptr(), t.data_ptr(), g.data_ptr(),
+                                      npos.data_ptr(), _stream(m))
+    _lib.check(rc, "b200det_cnt_loss_bwd")
+    _count("cnt_loss_bwd")
+    return grads
+
+
+def cls_loss_fwd(cls: Sequence[Tensor], mask_src: Tensor, cls_t: Tensor):
+    lib = _lib.load()
+    lv, keep_alive, p_total, batch, n = _levels(cls, None, None, [1] * len(cls))
+    m = _mask_src(mask_src, batch, p_total)
+    _need_cuda(cls_t, "cls target")
+    t = cls_t.to(torch.int64).reshape(batch, -1).contiguous()
+    assert t.shape[1] == p_total
+    ws_bytes = lib.b200det_cls_loss_workspace_bytes(batch, p_total)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=m.device)
+    loss = torch.empty((batch,), dtype=torch.float32, device=m.device)
+    npos = torch.empty_like(loss)
+    with torch.cuda.device(m.device):
+        rc = lib.b200det_cls_loss_fwd(lv, n, batch, keep_alive[0].shape[1], t.data_ptr(), m.data_ptr(),
+                                      ws.data_ptr(), ws_bytes, loss.data_ptr(), npos.data_ptr(), _stream(m))
+    _lib.check(rc, "b200det_cls_loss_fwd")
+    _count("cls_loss_fwd")
+    return loss, npos
+
+
+def cls_loss_bwd(cls: Sequence[Tensor], cls_t: Tensor, grad_loss: Tensor, npos: Tensor):
+    lib = _lib.load()
+    lv, keep_alive, p_total, batch, n = _levels(cls, None, None, [1] * len(cls))
+    t = cls_t.to(torch.int64).reshape(batch, -1).contiguous()
+    g = _f32c(grad_loss, "grad").reshape(batch)
+    grads = [torch.empty_like(x) for x in keep_alive]
+    with torch.cuda.device(g.device):
+        rc = lib.b200det_cls_loss_bwd(lv, _grad_ptrs(grads), n, batch, keep_alive[0].shape[1], t.data_ptr(),
+                                      g.data_ptr(), npos.data_ptr(), _stream(g))
+    _lib.check(rc, "b200det_cls_loss_bwd")
+    _count("cls_loss_bwd")
+    return grads
+
+
+# --------------------------------------------------------------------------------------------
+# torch.library registration: the same entry points as dispatcher ops, CUDA key only
+# --------------------------------------------------------------------------------------------
+_LIBDEF = torch.library.Library("b200det", "DEF")
+_LIBDEF.define("postprocess(Tensor[] cls, Tensor[] cnt, Tensor[] reg, int[] strides, float score_thr, "
+               "float nms_thr, int max_box, int clip_h, int clip_w) -> (Tensor, Tensor, Tensor, Tensor, Tensor)")
+_LIBDEF.define("batched_nms(Tensor boxes, Tensor scores, Tensor classes, float score_thr, float nms_thr, "
+               "int clip_h, int clip_w) -> (Tensor, Tensor, Tensor, Tensor, Tensor)")
+_LIBDEF.define("assign_targets(int[] level_hw, int[] strides, float[] limit_lo, float[] limit_hi, "
+               "Tensor gt_boxes, Tensor labels, float sample_radius) -> (Tensor, Tensor, Tensor)")
+_LIBDEF.define("clip_boxes_(Tensor(a!) boxes, int img_h, int img_w) -> Tensor(a!)")
+
+
+def _op_postprocess(cls, cnt, reg, strides, score_thr, nms_thr, max_box, clip_h, clip_w):
+    return postprocess(cls, cnt, reg, strides, score_thr, nms_thr, max_box, (clip_h, clip_w) if clip_h > 0 else None)
+
+
+def _op_batched_nms(boxes, scores, classes, score_thr, nms_thr, clip_h, clip_w):
+    return batched_nms(boxes, scores, classes, score_thr, nms_thr, None, (clip_h, clip_w) if clip_h > 0 else None)
+
+
+def _op_assign(level_hw, strides, limit_lo, limit_hi, gt_boxes, labels, sample_radius):
+    hw = [(level_hw[2 * i], level_hw[2 * i + 1]) for i in range(len(strides))]
+    return assign_targets(hw, strides, list(zip(limit_lo, limit_hi)), gt_boxes, labels, sample_radius)
+
+
+_LIBDEF.impl("postprocess", _op_postprocess, "CUDA")
+_LIBDEF.impl("batched_nms", _op_batched_nms, "CUDA")
+_LIBDEF.impl("assign_targets", _op_assign, "CUDA")
+_LIBDEF.impl("clip_boxes_", clip_boxes_, "CUDA")

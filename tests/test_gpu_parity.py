@@ -1,0 +1,417 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+fixtures produced by the unmodified reference.  Run on the B200 box with ``-m gpu``.
+
+Tolerances (BASELINE.json north_star): integers (keep indices, labels, GT indices) bit-exact on
+identical stage inputs; boxes / scores / losses within 1e-5 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fcos_oracle as O
+from pytorch_object_detection_b200 import workloads as W
+from helpers import REL_TOL, assert_close, assert_detections_match, assert_equal_int, load_golden, to_np
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import pytorch_object_detection_b200 as P
+    from pytorch_object_detection_b200 import ops
+DEV = "cuda:0"
+
+
+def cuda_levels(x):
+    return [[t.to(DEV) for t in part] for part in x]
+
+
+HEAD_CASES = {
+    "head_voc_b1": (W.VOC_LEVELS, W.VOC_HW),
+    "head_voc_4strides": (W.VOC_LEVELS, W.VOC_HW),
+    "head_coco_b2": (W.COCO_LEVELS, W.COCO_HW),
+    "head_coco_crowded": (W.COCO_LEVELS, W.COCO_HW),
+    "head_voc_k300": (W.VOC_LEVELS, W.VOC_HW),
+}
+
+
+def head_case(name):
+    levels, img_hw = HEAD_CASES[name]
+    g = load_golden(name)
+    batch, ncls, seed, max_box, crowded = (int(v) for v in g["meta"][:5])
+    x = W.head_outputs(batch, ncls, levels, seed, crowded=bool(crowded))
+    return g, x, batch, max_box, [int(s) for s in g["strides"]], img_hw
+
+
+# ------------------------------------------------------------------------------------------
+# K1: score / argmax
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["head_voc_b1", "head_coco_b2", "head_voc_4strides"])
+def test_score_points_matches_oracle(name):
+    g, x, batch, max_box, strides, _ = head_case(name)
+    want_s, want_c, _ = O.score_points(x, strides)
+    xc = cuda_levels(x)
+    got_s, got_c = ops.score_points(xc[0], xc[1], strides)
+    assert got_s.shape == want_s.shape
+    assert_close(to_np(got_s), to_np(want_s), REL_TOL, what="score")
+    # argmax over logits == argmax over sigmoid unless two logits round to one fp32 sigmoid
+    assert_equal_int(to_np(got_c).astype(np.int64) + 1, to_np(want_c), what="class")
+
+
+# ------------------------------------------------------------------------------------------
+# K2: top-k on IDENTICAL scores (the oracle's), tie-aware order, boxes bit-exact
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["head_voc_b1", "head_coco_b2", "head_voc_k300"])
+def test_select_topk_on_identical_scores(name):
+    g, x, batch, max_box, strides, _ = head_case(name)
+    score, classes, boxes = O.score_points(x, strides)
+    s_k, c_k, b_k, idx = O.select_topk(score, classes, boxes, max_box)
+    xc = cuda_levels(x)
+    gs, gc, gb, gp, gn = ops.select_topk(xc[2], strides, score.to(DEV).contiguous(),
+                                         (classes - 1).to(torch.int16).to(DEV).contiguous(), 0.05, max_box)
+    for b in range(batch):
+        m = s_k[b] >= 0.05
+        n = int(m.sum())
+        assert int(gn[b]) == n
+        assert_detections_match((to_np(gs[b, :n]), to_np(gc[b, :n]), to_np(gb[b, :n])),
+                                (to_np(s_k[b][m]), to_np(c_k[b][m]), to_np(b_k[b][m])), rel=0.0,
+                                what=f"{name} top-k img {b}")
+        # our tie rule: score desc, point index asc
+        pts = to_np(gp[b, :n]).astype(np.int64)
+        sc = to_np(gs[b, :n]).astype(np.float64)
+        order = np.lexsort((pts, -sc))
+        assert np.array_equal(order, np.arange(n))
+        assert np.array_equal(np.sort(pts), np.sort(to_np(idx[b][m])))
+
+
+def test_select_topk_all_equal_scores_takes_lowest_indices():
+    levels = [(8, 8), (4, 4)]
+    strides = [8, 16]
+    p = W.num_points(levels)
+    reg = [torch.rand(2, 4, h, w, device=DEV) * 20 + 1 for h, w in levels]
+    score = torch.full((2, p), 0.25, device=DEV)
+    score[1, 10:30] = 0.5
+    cls0 = torch.zeros((2, p), dtype=torch.int16, device=DEV)
+    gs, gc, gb, gp, gn = ops.select_topk(reg, strides, score, cls0, 0.05, 16)
+    assert gn.tolist() == [16, 16]
+    assert gp[0].tolist() == list(range(16))
+    assert gp[1].tolist() == list(range(10, 26))
+    gs, gc, gb, gp, gn = ops.select_topk(reg, strides, score, cls0, 0.3, 50)
+    assert gn.tolist() == [0, 20]
+    assert gp[1, :20].tolist() == list(range(10, 30))
+    # k larger than P: everything above the threshold, sorted
+    gs, gc, gb, gp, gn = ops.select_topk(reg, strides, score, cls0, 0.05, 1000)
+    assert gn.tolist() == [p, p]
+    assert gp[1, :20].tolist() == list(range(10, 30))
+
+
+# ------------------------------------------------------------------------------------------
+# K3: NMS keep indices bit-exact against torchvision's CPU op (golden) on identical inputs
+# ------------------------------------------------------------------------------------------
+def run_nms(boxes, scores, classes, thr, score_thr=-1e30, clip=None):
+    s, c, b, k, n = ops.batched_nms(boxes[None].to(DEV), scores[None].to(DEV), classes[None].to(DEV), score_thr, thr,
+                                    None, clip)
+    n = int(n[0])
+    return to_np(s[0, :n]), to_np(c[0, :n]), to_np(b[0, :n]), to_np(k[0, :n])
+
+
+def test_nms_matches_torchvision_golden():
+    g = load_golden("nms_cases")
+    names = sorted({k.rsplit("_", 1)[0] for k in g.files if k.endswith("_keep")})
+    for nme in names:
+        boxes = torch.from_numpy(g[nme + "_boxes"])
+        scores = torch.from_numpy(g[nme + "_scores"])
+        classes = torch.from_numpy(g[nme + "_classes"]).long()
+        s, c, b, keep = run_nms(boxes, scores, classes, float(g[nme + "_thr"]))
+        want = g[nme + "_keep"].astype(np.int64)
+        if nme in ("crowd5000", "crowd1001"):   # vanilla branch: torch's final sort is unstable on ties
+            assert np.array_equal(np.sort(keep), np.sort(want)), nme
+            assert_close(scores.numpy()[keep], scores.numpy()[want], rel=0.0, what=nme)
+        else:
+            assert_equal_int(keep, want, what=nme)
+        assert np.array_equal(s, scores.numpy()[keep])
+        assert np.array_equal(c, classes.numpy()[keep])
+        assert np.array_equal(b, boxes.numpy()[keep])
+
+
+@pytest.mark.parametrize("seed,n,ncls", [(1, 300, 4), (2, 999, 80), (3, 1000, 20), (4, 1500, 10), (5, 64, 2),
+                                         (6, 65, 2), (7, 2048, 3), (8, 5000, 80)])
+def test_nms_matches_oracle_random(seed, n, ncls):
+    boxes, scores, classes = W.crowd_candidates(n, ncls, seed=seed, clusters=8)
+    boxes[::7] -= 600.0          # negative coordinates: cross-class suppression on the trick branch
+    want = O.batched_nms(boxes, scores, classes, 0.6).numpy()
+    _, _, _, keep = run_nms(boxes, scores, classes, 0.6)
+    assert_equal_int(keep, want, what=f"n={n}")
+
+
+def test_nms_threshold_ragged_batch_and_clip():
+    b0, s0, c0 = W.crowd_candidates(500, 5, seed=41, clusters=5)
+    b1, s1, c1 = W.crowd_candidates(500, 5, seed=42, clusters=5)
+    boxes, scores, classes = torch.stack([b0, b1]), torch.stack([s0, s1]), torch.stack([c0, c1])
+    in_count = torch.tensor([500, 123], dtype=torch.int32)
+    s, c, b, k, n = ops.batched_nms(boxes.to(DEV), scores.to(DEV), classes.to(DEV), 0.4, 0.5, in_count.to(DEV),
+                                    (832, 1344))
+    for i, cnt in enumerate([500, 123]):
+        want = O.post_process_image(scores[i, :cnt], classes[i, :cnt], boxes[i, :cnt], 0.4, 0.5)
+        m = int(n[i])
+        assert m == want[0].numel()
+        assert_equal_int(to_np(k[i, :m]), to_np(want[3]), what="keep")
+        assert np.array_equal(to_np(s[i, :m]), to_np(want[0]))
+        clipped = O.clip_boxes_(want[2].clone(), 832, 1344)
+        assert np.array_equal(to_np(b[i, :m]), to_np(clipped))
+    # nothing above the threshold
+    s, c, b, k, n = ops.batched_nms(boxes.to(DEV), scores.to(DEV), classes.to(DEV), 2.0, 0.5)
+    assert n.tolist() == [0, 0]
+
+
+# ------------------------------------------------------------------------------------------
+# whole head against the reference's outputs (golden)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(HEAD_CASES))
+def test_head_matches_reference_golden(name):
+    g, x, batch, max_box, strides, img_hw = head_case(name)
+    head = P.FCOSHead(0.05, 0.6, max_box, strides)
+    xc = cuda_levels(x)
+    s, c, b, n = head.detect(xc)
+    s2, c2, b2, n2 = head.detect(xc, clip_hw=img_hw)
+    for i in range(batch):
+        m = int(n[i])
+        assert_detections_match((to_np(s[i, :m]), to_np(c[i, :m]), to_np(b[i, :m])),
+                                (g[f"score_{i}"], g[f"class_{i}"], g[f"box_{i}"]), rel=REL_TOL, what=f"{name} img {i}")
+        assert int(n2[i]) == m
+        assert_detections_match((to_np(s2[i, :m]), to_np(c2[i, :m]), to_np(b2[i, :m])),
+                                (g[f"score_{i}"], g[f"class_{i}"], g[f"clipped_{i}"]), rel=REL_TOL,
+                                what=f"{name} clipped img {i}")
+    if batch == 1:     # the drop-in forward + ClipBoxes, exactly as test.py:206-207 calls them
+        fs, fc, fb = head(xc)
+        assert fs.shape == (1, int(n[0])) and fc.dtype == torch.int64 and fb.shape == (1, int(n[0]), 4)
+        imgs = torch.zeros(1, 3, *img_hw, device=DEV)
+        out = P.ClipBoxes()(imgs, fb)
+        assert out.data_ptr() == fb.data_ptr()
+        assert_detections_match((to_np(fs[0]), to_np(fc[0]), to_np(fb[0])),
+                                (g["score_0"], g["class_0"], g["clipped_0"]), rel=REL_TOL, what=name + " forward")
+
+
+def test_head_ragged_batch_raises_like_reference_and_empty_result():
+    x = cuda_levels(W.head_outputs(2, 20, W.VOC_LEVELS, seed=77))
+    x[0][0][1] -= 3.0                          # image 1 keeps fewer boxes
+    head = P.FCOSHead(0.05, 0.6, 1000, W.STRIDES)
+    s, c, b, n = head.detect(x)
+    assert n[0] != n[1]
+    with pytest.raises(RuntimeError, match="stack expects each tensor to be equal size"):
+        head(x)
+    x1 = [[t[:1] for t in part] for part in x]
+    fs, fc, fb = P.FCOSHead(0.99, 0.6, 1000, W.STRIDES)(x1)
+    assert fs.shape == (1, 0) and fc.shape == (1, 0) and fc.dtype == torch.int64 and fb.shape == (1, 0, 4)
+    with pytest.raises(Exception):
+        head([[t.cpu() for t in part] for part in x1])     # no CPU path
+
+
+def test_post_process_entry_matches_oracle():
+    g, x, batch, max_box, strides, _ = head_case("head_voc_b1")
+    score, classes, boxes = O.score_points(x, strides)
+    s_k, c_k, b_k, _ = O.select_topk(score, classes, boxes, max_box)
+    want = O.post_process_image(s_k[0], c_k[0], b_k[0], 0.05, 0.6)
+    got = P.FCOSHead(0.05, 0.6, max_box, strides).post_process([s_k.to(DEV), c_k.to(DEV), b_k.to(DEV)])
+    assert np.array_equal(to_np(got[0][0]), to_np(want[0]))
+    assert np.array_equal(to_np(got[1][0]), to_np(want[1]))
+    assert np.array_equal(to_np(got[2][0]), to_np(want[2]))
+
+
+# ------------------------------------------------------------------------------------------
+# K4a: target assignment, bit-exact against the reference (golden)
+# ------------------------------------------------------------------------------------------
+TRAIN_CASES = {
+    "train_voc_b2": (W.VOC_LEVELS, W.VOC_HW),
+    "train_coco_b2": (W.COCO_LEVELS, W.COCO_HW),
+    "train_voc_dense": (W.VOC_LEVELS, W.VOC_HW),
+}
+
+
+def ieee_centerness(reg_t, cnt_ref):
+    """Centerness recomputed from reg targets with numpy fp32 (every op correctly rounded, as CUDA's
+    __fsqrt_rn/__fdiv_rn are).  torch's CPU sqrt goes through MKL VML and is off by 1 ulp on ~0.6 %
+    of inputs, so the reference's CPU cnt_t is matched to 1 ulp and this IEEE value bit-exactly."""
+    r = np.asarray(reg_t, dtype=np.float32)
+    f = np.float32
+    lr_min, lr_max = np.minimum(r[..., 0], r[..., 2]), np.maximum(r[..., 0], r[..., 2])
+    tb_min, tb_max = np.minimum(r[..., 1], r[..., 3]), np.maximum(r[..., 1], r[..., 3])
+    with np.errstate(invalid="ignore"):
+        c = np.sqrt((lr_min * tb_min) / (lr_max * tb_max + f(1e-10)), dtype=np.float32)
+    return np.where(np.asarray(cnt_ref)[..., 0] > -1, c, f(-1))[..., None]
+
+
+def assert_cnt_matches(got, ref_cnt, ref_reg):
+    got = to_np(got)
+    assert np.array_equal(got > -1, np.asarray(ref_cnt) > -1), "positive sets differ"
+    assert np.array_equal(got, ieee_centerness(ref_reg, ref_cnt)), "cnt_t differs from the IEEE evaluation"
+    assert_close(got, ref_cnt, rel=2e-7, what="cnt_t vs reference CPU (1 ulp: MKL sqrt)")
+
+
+def train_case(name):
+    levels, img_hw = TRAIN_CASES[name]
+    g = load_golden(name)
+    batch, ncls, seed, max_gt = (int(v) for v in g["meta"][:4])
+    gt, labels = W.gt_boxes(batch, max_gt, img_hw, ncls, seed)
+    x = W.head_outputs(batch, ncls, levels, seed + 1)
+    return g, x, gt, labels, g["ranges"].tolist(), levels
+
+
+@pytest.mark.parametrize("name", sorted(TRAIN_CASES))
+def test_assign_targets_bit_exact(name):
+    g, x, gt, labels, ranges, levels = train_case(name)
+    gen = P.FCOSGenTargets(W.STRIDES, ranges)
+    cls_t, cnt_t, reg_t = gen([cuda_levels(x), gt.to(DEV), labels.to(DEV)])
+    assert cls_t.dtype == torch.int64 and cls_t.shape == (gt.shape[0], W.num_points(levels), 1)
+    assert_equal_int(to_np(cls_t), g["cls_t"], what="cls_t")
+    assert np.array_equal(to_np(reg_t), g["reg_t"]), "reg_t not bit-exact"
+    assert_cnt_matches(cnt_t, g["cnt_t"], g["reg_t"])
+    # GT index against the oracle
+    _, _, _, want_idx = O.assign_targets(levels, gt, labels, W.STRIDES, ranges)
+    out = ops.assign_targets(levels, W.STRIDES, ranges, gt.to(DEV), labels.to(DEV), want_index=True)
+    assert_equal_int(to_np(out[3]), to_np(want_idx), what="gt index")
+    # single-level static entry point (head.py:235)
+    lv = 1
+    one = P.FCOSGenTargets.generate_target([t[lv].to(DEV) for t in x], gt.to(DEV), labels.to(DEV), W.STRIDES[lv],
+                                           ranges[lv])
+    o0 = sum(h * w for h, w in levels[:lv])
+    o1 = o0 + levels[lv][0] * levels[lv][1]
+    assert np.array_equal(to_np(one[0]), g["cls_t"][:, o0:o1].astype(np.int64))
+    assert np.array_equal(to_np(one[2]), g["reg_t"][:, o0:o1])
+
+
+def test_assign_targets_full_size_config3():
+    """BASELINE config 3 at full size (B=32, P=23265, M<=100) against the oracle."""
+    gt, labels = W.gt_boxes(32, 100, W.COCO_HW, 80, seed=301)
+    want = O.assign_targets(W.COCO_LEVELS, gt, labels, W.STRIDES, W.HISFCOS_RANGES)
+    got = ops.assign_targets(W.COCO_LEVELS, W.STRIDES, W.HISFCOS_RANGES, gt.to(DEV), labels.to(DEV), want_index=True)
+    assert_equal_int(to_np(got[0]), to_np(want[0]), what="cls_t")
+    assert np.array_equal(to_np(got[2]), to_np(want[2]))
+    assert_cnt_matches(got[1], to_np(want[1]), to_np(want[2]))
+    assert_equal_int(to_np(got[3]), to_np(want[3]), what="gt index")
+    assert int((got[1] > -1).sum()) > 1000
+
+
+def test_assign_targets_edge_cases():
+    # no ground truth at all (all padding), one GT, and GT ties (identical boxes -> lowest index wins)
+    gt = torch.full((3, 4, 4), -1.0)
+    labels = torch.full((3, 4), -1, dtype=torch.int64)
+    gt[1, 0] = torch.tensor([100.0, 120.0, 300.0, 260.0]); labels[1, 0] = 7
+    gt[2, 1] = torch.tensor([50.0, 50.0, 250.0, 250.0]); labels[2, 1] = 3
+    gt[2, 3] = torch.tensor([50.0, 50.0, 250.0, 250.0]); labels[2, 3] = 9
+    want = O.assign_targets(W.VOC_LEVELS, gt, labels, W.STRIDES, W.FCOS_RANGES)
+    got = ops.assign_targets(W.VOC_LEVELS, W.STRIDES, W.FCOS_RANGES, gt.to(DEV), labels.to(DEV), want_index=True)
+    for j in (0, 2, 3):
+        assert np.array_equal(to_np(got[j]).astype(np.float64), to_np(want[j]).astype(np.float64))
+    assert_cnt_matches(got[1], to_np(want[1]), to_np(want[2]))
+    assert int((got[0][0] != 0).sum()) == 0
+    assert set(to_np(got[3][2]).tolist()) <= {-1, 1}
+
+
+# ------------------------------------------------------------------------------------------
+# K4b: losses and gradients against the reference (golden)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(TRAIN_CASES))
+@pytest.mark.parametrize("mode", ["giou", "iou"])
+def test_losses_and_gradients_match_reference(name, mode):
+    g, x, gt, labels, ranges, levels = train_case(name)
+    xc = cuda_levels(x)
+    for part in xc:
+        for t in part:
+            t.requires_grad_(True)
+    tgt = P.FCOSGenTargets(W.STRIDES, ranges)([xc, gt.to(DEV), labels.to(DEV)])
+    losses = P.FCOSLoss(mode)([xc, tgt])
+    assert all(v.dim() == 0 for v in losses)
+    assert_close([float(v) for v in losses], g[f"loss_{mode}"], rel=REL_TOL, what=f"loss {mode}")
+    losses[3].backward()
+    for lv in range(len(levels)):
+        assert_close(to_np(xc[2][lv].grad), g[f"g_reg_{mode}_{lv}"], rel=REL_TOL, abs_=1e-9, what=f"g_reg {lv}")
+        assert_close(to_np(xc[1][lv].grad), g[f"g_cnt_{mode}_{lv}"], rel=REL_TOL, abs_=1e-9, what=f"g_cnt {lv}")
+        if f"g_cls_{mode}_{lv}" in g.files:
+            assert_close(to_np(xc[0][lv].grad), g[f"g_cls_{mode}_{lv}"], rel=REL_TOL, abs_=1e-12, what=f"g_cls {lv}")
+        else:
+            assert_close(to_np(xc[0][lv].grad.double().sum(dim=(2, 3))), g[f"g_cls_sum_{mode}_{lv}"], rel=1e-4,
+                         abs_=1e-9, what=f"g_cls sums {lv}")
+
+
+def test_known_answer_and_free_functions():
+    """model/loss.py:219-221 prints tensor([0.3133, 0.3133]); analytic IoU/GIoU values."""
+    got = P.compute_cnt_loss([torch.ones(2, 1, 4, 4, device=DEV)] * 5, torch.ones(2, 80, 1, device=DEV),
+                             torch.ones(2, 80, dtype=torch.bool, device=DEV))
+    assert_close(to_np(got), load_golden("known_answers")["cnt_loss_ones"], rel=1e-6)
+    assert [round(float(v), 4) for v in got] == [0.3133, 0.3133]
+    same = torch.tensor([[3.0, 4.0, 5.0, 6.0]], device=DEV)
+    assert float(P.giou_loss(same, same)) == pytest.approx(0.0, abs=1e-6)
+    inner = torch.tensor([[5.0, 5.0, 5.0, 5.0]], device=DEV, requires_grad=True)
+    outer = torch.tensor([[10.0, 10.0, 10.0, 10.0]], device=DEV)
+    gl = P.giou_loss(inner, outer)
+    assert float(gl) == pytest.approx(0.75, rel=1e-6)
+    assert float(P.iou_loss(inner, outer)) == pytest.approx(-np.log(0.25), rel=1e-6)
+    gl.backward()
+    ref_in = torch.tensor([[5.0, 5.0, 5.0, 5.0]], requires_grad=True)
+    O.giou_sum(ref_in, outer.cpu()).backward()
+    assert_close(to_np(inner.grad), to_np(ref_in.grad), rel=REL_TOL)
+    with pytest.raises(NotImplementedError):
+        P.compute_reg_loss([torch.ones(1, 4, 2, 2, device=DEV)], torch.ones(1, 4, 4, device=DEV),
+                           torch.ones(1, 4, dtype=torch.bool, device=DEV), mode="diou")
+    # focal_loss_from_logits on [P, C] logits / one-hot
+    torch.manual_seed(0)
+    logits = torch.randn(37, 6) - 2
+    hot = torch.zeros(37, 6); hot[torch.arange(0, 37, 3), torch.arange(0, 37, 3) % 6] = 1
+    assert_close(float(P.focal_loss_from_logits(logits.to(DEV), hot.to(DEV))), float(O.focal_sum(logits, hot)),
+                 rel=REL_TOL)
+
+
+def test_box_loss_tie_subgradients_match_autograd():
+    """Exact min/max ties (pred == target component) split the gradient 1/2-1/2 like torch."""
+    p = torch.tensor([[4.0, 6.0, 8.0, 3.0], [2.0, 2.0, 2.0, 2.0], [1.0, 9.0, 4.0, 4.0]])
+    t = torch.tensor([[4.0, 5.0, 8.0, 7.0], [2.0, 2.0, 2.0, 2.0], [3.0, 9.0, 1.0, 4.0]])
+    for fn_gpu, fn_cpu in ((P.giou_loss, O.giou_sum), (P.iou_loss, O.iou_sum)):
+        a = p.clone().to(DEV).requires_grad_(True)
+        b = p.clone().requires_grad_(True)
+        fn_gpu(a, t.to(DEV)).backward()
+        fn_cpu(b, t).backward()
+        assert_close(to_np(a.grad), to_np(b.grad), rel=REL_TOL, abs_=1e-9)
+
+
+# ------------------------------------------------------------------------------------------
+# full-size configs: properties that do not need the oracle at scale + oracle spot checks
+# ------------------------------------------------------------------------------------------
+def test_full_size_config2_postprocess_properties_and_oracle():
+    """BASELINE config 2: COCO 832x1344, 80 classes, batch 16."""
+    x = W.head_outputs(16, 80, W.COCO_LEVELS, seed=202)
+    head = P.FCOSHead(0.05, 0.6, 1000, W.STRIDES)
+    xc = cuda_levels(x)
+    s, c, b, n = head.detect(xc)
+    want = O.detect(x, 0.05, 0.6, 1000, W.STRIDES)
+    for i in range(16):
+        m = int(n[i])
+        assert_detections_match((to_np(s[i, :m]), to_np(c[i, :m]), to_np(b[i, :m])),
+                                tuple(to_np(t) for t in want[i]), rel=REL_TOL, what=f"img {i}")
+    # idempotence: NMS of the survivors keeps everything, in the same order
+    s2, c2, b2, k2, n2 = ops.batched_nms(b, s, c, 0.05, 0.6, n)
+    assert torch.equal(n2, n)
+    for i in range(16):
+        m = int(n[i])
+        assert torch.equal(k2[i, :m], torch.arange(m, device=DEV))
+        assert torch.equal(b2[i, :m], b[i, :m])
+    # per-image independence: image 5 alone gives the same answer as inside the batch
+    s1, c1, b1, n1 = head.detect([[t[5:6] for t in part] for part in xc])
+    m = int(n[5])
+    assert int(n1[0]) == m and torch.equal(s1[0, :m], s[5, :m]) and torch.equal(b1[0, :m], b[5, :m])
+
+
+def test_full_size_config4_dense_crowd():
+    """BASELINE config 4: 5 x 1000 candidates per image (vanilla per-class branch), IoU 0.6."""
+    boxes, scores, classes = zip(*[W.crowd_candidates(5000, 80, seed=400 + i) for i in range(4)])
+    boxes, scores, classes = torch.stack(boxes), torch.stack(scores), torch.stack(classes)
+    s, c, b, k, n = ops.batched_nms(boxes.to(DEV), scores.to(DEV), classes.to(DEV), 0.05, 0.6)
+    for i in range(4):
+        want = O.post_process_image(scores[i], classes[i], boxes[i], 0.05, 0.6)
+        m = int(n[i])
+        assert m == want[0].numel()
+        assert_equal_int(to_np(k[i, :m]), to_np(want[3]), what=f"keep img {i}")
+    # 300 GT boxes per image for assignment (dense-crowd training side)
+    gt, labels = W.gt_boxes(8, 300, W.COCO_HW, 80, seed=404)
+    want = O.assign_targets(W.COCO_LEVELS, gt, labels, W.STRIDES, W.HISFCOS_RANGES)
+    got = ops.assign_targets(W.COCO_LEVELS, W.STRIDES, W.HISFCOS_RANGES, gt.to(DEV), labels.to(DEV), want_index=True)
+    assert_equal_int(to_np(got[3]), to_np(want[3]), what="gt index")
+    assert np.array_equal(to_np(got[2]), to_np(want[2]))
