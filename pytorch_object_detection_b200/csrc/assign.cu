@@ -28,10 +28,12 @@ struct AssignTable {
 
 struct GtEntry {
   float x0, y0, x1, y1;
+  float cx, cy;          // (x0+x1)/2, (y0+y1)/2 as the reference rounds them (head.py:276-277)
   int idx;
+  int pad_;
 };
 
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 4)
 assign_targets_kernel(const AssignTable at, const int M, const float* __restrict__ gt_boxes,
                       const long long* __restrict__ gt_labels, long long* __restrict__ cls_t,
                       float* __restrict__ cnt_t, float* __restrict__ reg_t, int32_t* __restrict__ gt_index) {
@@ -52,17 +54,21 @@ assign_targets_kernel(const AssignTable at, const int M, const float* __restrict
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
   {
-    // rows covered by this tile -> y range; keep boxes whose centre row can pass the centre mask.
-    // The margin of 1 px dwarfs any fp32 rounding of (y0+y1)/2 or y-cy at image-scale coordinates.
+    // Conservative, rounding-safe pre-filter (margins of 1 px dwarf any fp32 rounding at image scale):
+    //  * rows covered by this tile -> y range; the centre mask needs |y - cy| < radius;
+    //  * a point strictly inside a box has max(l,t,r,b) in [max(w,h)/2, max(w,h)), so the level's
+    //    (lo, hi] range can only be met when max(w,h) > lo and max(w,h)/2 <= hi.
     const float ymin = (float)((t0 / w) * s + half) - radius - 1.0f;
     const float ymax = (float)((t1 / w) * s + half) + radius + 1.0f;
     const float4* g4 = reinterpret_cast<const float4*>(gt_boxes) + (size_t)b * M;
     for (int m = threadIdx.x; m < M; m += kTileThreads) {
       const float4 g = g4[m];
+      const float cx = __fmul_rn(__fadd_rn(g.x, g.z), 0.5f);
       const float cy = __fmul_rn(__fadd_rn(g.y, g.w), 0.5f);
-      if (cy >= ymin && cy <= ymax) {
+      const float side = fmaxf(g.z - g.x, g.w - g.y);
+      if (cy >= ymin && cy <= ymax && side > lo - 1.0f && 0.5f * side <= hi + 1.0f) {
         const int at_ = atomicAdd(&s_n, 1);
-        list[at_] = GtEntry{g.x, g.y, g.z, g.w, m};
+        list[at_] = GtEntry{g.x, g.y, g.z, g.w, cx, cy, m, 0};
       }
     }
   }
@@ -70,26 +76,31 @@ assign_targets_kernel(const AssignTable at, const int M, const float* __restrict
   const int n_list = s_n;
 
   const size_t out0 = (size_t)b * at.num_points + at.point_off[l];
+  const float inv_w = 1.0f / (float)w;
 #pragma unroll
   for (int q = 0; q < kTilePts; ++q) {
     const int pos = t0 + threadIdx.x + q * kTileThreads;    // strided: every store instruction is coalesced
     if (pos >= hw) break;
-    const float x = (float)((pos % w) * s + half);
-    const float y = (float)((pos / w) * s + half);
+    int row = (int)((float)pos * inv_w);                    // estimate within +-1, then fix up exactly
+    int col = pos - row * w;
+    if (col < 0) { --row; col += w; }
+    if (col >= w) { ++row; col -= w; }
+    const float x = (float)(col * s + half);
+    const float y = (float)(row * s + half);
     float best_area = CUDART_INF_F;
     int best_m = -1;
     float bl = -1.f, bt = -1.f, br = -1.f, bb = -1.f;
     for (int e = 0; e < n_list; ++e) {
       const GtEntry g = list[e];
+      // centre mask first (head.py:275-283): it rejects all but ~3x3 points per box.
+      // max(x-cx, y-cy, cx-x, cy-y) = max(|x-cx|, |y-cy|) exactly (fp32 subtraction is odd-symmetric)
+      const float cmax = fmaxf(fabsf(__fsub_rn(x, g.cx)), fabsf(__fsub_rn(y, g.cy)));
+      if (!(cmax < radius)) continue;
       const float lf = __fsub_rn(x, g.x0), tf = __fsub_rn(y, g.y0);
       const float rf = __fsub_rn(g.x1, x), bf = __fsub_rn(g.y1, y);
       const float omin = fminf(fminf(lf, tf), fminf(rf, bf));
       const float omax = fmaxf(fmaxf(lf, tf), fmaxf(rf, bf));
-      const float cx = __fmul_rn(__fadd_rn(g.x0, g.x1), 0.5f);
-      const float cy = __fmul_rn(__fadd_rn(g.y0, g.y1), 0.5f);
-      const float cmax = fmaxf(fmaxf(__fsub_rn(x, cx), __fsub_rn(y, cy)), fmaxf(__fsub_rn(cx, x), __fsub_rn(cy, y)));
-      const bool pos_ok = (omin > 0.f) && (omax > lo) && (omax <= hi) && (cmax < radius);
-      if (pos_ok) {
+      if ((omin > 0.f) && (omax > lo) && (omax <= hi)) {
         const float area = __fmul_rn(__fadd_rn(lf, rf), __fadd_rn(tf, bf));
         if (area < best_area || (area == best_area && g.idx < best_m)) {
           best_area = area;

@@ -227,6 +227,144 @@ nms_scan_kernel(const CandSet set, const int wcap, const unsigned long long* __r
   if (tid == 0) out.count[b] = total;
 }
 
+// ---- small-n variant: the image's whole upper-triangular mask resident in shared memory ------
+// (cap <= kSmemScanMaxCap, i.e. every reference configuration with max_detection_box = 1000).
+// All warps stage the rows with cp.async into a padded layout (odd row stride: a lane-per-row
+// column read is bank-conflict-free); then ONE warp runs the greedy pass with no block barrier
+// on its critical path:
+//   per 64-row block: lane i holds diagonal words of rows i and i+32.  If no still-alive row
+//   suppresses another still-alive row of the block (one warp OR-reduction) every alive row is
+//   kept at once; otherwise the 64 rows are resolved serially out of registers (shuffles).
+//   The kept rows are then OR-reduced column by column into the removed-bitmap, which lives in
+//   registers (lane w owns word w).
+constexpr int kSmemScanThreads = 256;
+constexpr int kSmemScanMaxCap = 1280;    // 1280 * 21 * 8 B = 210 KB
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
+  const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+  const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+  return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
+  const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);
+  const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+__global__ void __launch_bounds__(kSmemScanThreads, 1)
+nms_scan_smem_kernel(const CandSet set, const int wcap, const unsigned long long* __restrict__ mask,
+                     const int clip_h, const int clip_w, const NmsOut out) {
+  extern __shared__ __align__(16) unsigned long long sm[];   // [cap][stride] mask rows, [32] keep words
+  __shared__ int s_pre[33];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kSmemScanThreads / 32;
+  const int b = blockIdx.x;
+  const int n = set.count[b];
+  const int W = (n + kNmsTile - 1) / kNmsTile;              // <= 20
+  const int stride = wcap | 1;
+  unsigned long long* M = sm;
+  unsigned long long* keepw = sm + (size_t)set.cap * stride;
+  const size_t o0 = (size_t)b * set.cap;
+  const size_t q0 = (size_t)b * out.stride;
+
+  // stage rows [r0, r1): row i needs the words of its own block and the blocks ahead
+  auto stage_rows = [&](int r0, int r1) {
+    for (int i = r0 + warp; i < r1; i += kWarps)
+      for (int w = (i >> 6) + lane; w < W; w += 32)
+        cp_async8(M + (size_t)i * stride + w, mask + (o0 + i) * wcap + w);
+    cp_async_commit();
+  };
+  const int split = min(n, 4 * kNmsTile);
+  stage_rows(0, split);
+  stage_rows(split, n);
+  if (tid < 32) keepw[tid] = 0ull;
+  cp_async_wait<1>();
+  __syncthreads();                                           // rows [0, split) resident
+
+  if (warp != 0) {
+    cp_async_wait<0>();
+    asm volatile("bar.arrive 1, %0;" ::"n"(kSmemScanThreads) : "memory");
+  } else {
+    unsigned long long myrem = 0ull;                         // lane w: removed-bitmap word w
+    bool rest_ready = false;
+    for (int rb = 0; rb < W; ++rb) {
+      if (rb == 4) {
+        cp_async_wait<0>();
+        asm volatile("bar.sync 1, %0;" ::"n"(kSmemScanThreads) : "memory");
+        rest_ready = true;
+      }
+      const int base = rb * kNmsTile;
+      const int rows = min(kNmsTile, n - base);
+      const unsigned long long valid = rows == kNmsTile ? ~0ull : ((1ull << rows) - 1ull);
+      const unsigned long long cur = shfl64(myrem, rb);
+      const size_t r0 = (size_t)(base + lane) * stride, r1 = (size_t)(base + lane + 32) * stride;
+      const unsigned long long d0 = (lane < rows) ? M[r0 + rb] : 0ull;
+      const unsigned long long d1 = (lane + 32 < rows) ? M[r1 + rb] : 0ull;
+      const bool a0 = !((cur >> lane) & 1ull), a1 = !((cur >> (lane + 32)) & 1ull);
+      const unsigned long long S = warp_or64((a0 ? d0 : 0ull) | (a1 ? d1 : 0ull));
+      unsigned long long keep;
+      if (((S & ~cur) & valid) == 0ull) {
+        keep = ~cur & valid;                                 // no alive row touches another alive row
+      } else {
+        unsigned long long c = cur;
+        keep = 0ull;
+#pragma unroll 8
+        for (int i = 0; i < kNmsTile; ++i) {
+          const unsigned long long di = shfl64(i < 32 ? d0 : d1, i & 31);
+          const bool alive = ((valid >> i) & 1ull) && !((c >> i) & 1ull);
+          keep |= alive ? (1ull << i) : 0ull;
+          c |= alive ? di : 0ull;
+        }
+      }
+      if (lane == 0) keepw[rb] = keep;
+      const bool k0 = (keep >> lane) & 1ull, k1 = (keep >> (lane + 32)) & 1ull;
+      for (int w = rb + 1; w < W; ++w) {
+        const unsigned long long v = warp_or64((k0 ? M[r0 + w] : 0ull) | (k1 ? M[r1 + w] : 0ull));
+        if (lane == w) myrem |= v;
+      }
+    }
+    if (!rest_ready) {
+      cp_async_wait<0>();
+      asm volatile("bar.sync 1, %0;" ::"n"(kSmemScanThreads) : "memory");
+    }
+  }
+  __syncthreads();
+
+  if (warp == 0) {                                           // exclusive prefix of kept counts per block
+    const int cnt = (lane < W) ? __popcll(keepw[lane]) : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    s_pre[lane] = incl - cnt;
+    if (lane == 31) s_pre[32] = incl;
+  }
+  __syncthreads();
+  for (int q = tid; q < n; q += kSmemScanThreads) {
+    const unsigned long long kw = keepw[q >> 6];
+    if (!((kw >> (q & 63)) & 1ull)) continue;
+    const int o = s_pre[q >> 6] + __popcll(kw & ((1ull << (q & 63)) - 1ull));
+    float4 bx = reinterpret_cast<const float4*>(set.box)[o0 + q];
+    if (clip_h > 0) {   // ClipBoxes: clamp_(min=0), then x <= w-1, y <= h-1   (head.py:156-162)
+      bx.x = clip1(bx.x, (float)(clip_w - 1));
+      bx.y = clip1(bx.y, (float)(clip_h - 1));
+      bx.z = clip1(bx.z, (float)(clip_w - 1));
+      bx.w = clip1(bx.w, (float)(clip_h - 1));
+    }
+    out.score[q0 + o] = set.score[o0 + q];
+    out.cls[q0 + o] = (long long)set.cls[o0 + q];
+    out.keep[q0 + o] = (long long)set.src[o0 + q];
+    reinterpret_cast<float4*>(out.box)[q0 + o] = bx;
+  }
+  if (tid == 0) out.count[b] = s_pre[32];
+}
+
 struct NmsWorkspace {
   CandSet set;
   unsigned long long* mask;
@@ -277,6 +415,16 @@ int launch_nms(const CandSet& set, int batch, double nms_thr, int clip_h, int cl
   nms_mask_kernel<<<dim3(wblocks, wblocks, batch), kNmsTile, 0, stream>>>(set, wcap, thr_up, zero_suppresses, mask);
   int rc = check_launch();
   if (rc) return rc;
+  if (set.cap <= kSmemScanMaxCap) {
+    const size_t smem = ((size_t)set.cap * (wcap | 1) + 32) * sizeof(unsigned long long);
+    if (smem > 48 * 1024) {
+      cudaError_t e =
+          cudaFuncSetAttribute(nms_scan_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
+    }
+    nms_scan_smem_kernel<<<batch, kSmemScanThreads, smem, stream>>>(set, wcap, mask, clip_h, clip_w, out);
+    return check_launch();
+  }
   const size_t smem = ((size_t)2 * kNmsTile * wcap + wcap) * sizeof(unsigned long long);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

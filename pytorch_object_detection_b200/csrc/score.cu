@@ -21,7 +21,7 @@ __device__ __forceinline__ void upd(float& best, int& arg, float v, int c) {
   }
 }
 
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 4)
 score_points_kernel(const LevelTable lt, const int C, float* __restrict__ score, int16_t* __restrict__ cls0) {
   const int b = blockIdx.y;
   const int l = level_of_tile(lt, blockIdx.x);
@@ -73,7 +73,20 @@ score_points_kernel(const LevelTable lt, const int C, float* __restrict__ score,
       in[q] = pos[q] < hw;
     }
     if (!in[0]) return;
-    for (int c = 0; c < C; ++c) {
+    int c = 0;
+    for (; c + kUnroll <= C; c += kUnroll) {       // same batching as the vector path: loads first
+      float v[kUnroll][4];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          v[u][q] = in[q] ? ldg_stream_f1(cls + (size_t)(c + u) * hw + pos[q]) : -CUDART_INF_F;
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) upd(best[q], arg[q], v[u][q], c + u);
+    }
+    for (; c < C; ++c) {
       const float* p = cls + (size_t)c * hw;
 #pragma unroll
       for (int q = 0; q < 4; ++q)

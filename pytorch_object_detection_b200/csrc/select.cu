@@ -74,11 +74,17 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
   uint32_t key[REG ? kSelItems : 1];
   int nv = 0;
   uint32_t kmin = 0xffffffffu, kmax = 0u;
-  if (REG) {
+  if constexpr (REG) {
+    float sv[kSelItems];                 // all loads issued before the first use: one memory round trip
 #pragma unroll
     for (int j = 0; j < kSelItems; ++j) {
       const int i = tid + j * kSelThreads;
-      key[j] = (i < P) ? load_key(sc, i, thr) : 0u;
+      sv[j] = (i < P) ? ldg_stream_f1(sc + i) : -CUDART_INF_F;
+    }
+#pragma unroll
+    for (int j = 0; j < kSelItems; ++j) {
+      const int i = tid + j * kSelThreads;
+      key[j] = (i < P && sv[j] >= thr) ? order_key(sv[j]) : 0u;
     }
   }
   FOR_KEYS(if (kx) { ++nv; kmin = min(kmin, kx); kmax = max(kmax, kx); })
@@ -143,15 +149,11 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
     sortbuf[at++] = ((unsigned long long)kx << 32) | (unsigned long long)(0xffffffffu - (uint32_t)ix);
   })
   const int n2 = next_pow2(kk);
-  for (int i = kk + tid; i < n2; i += kSelThreads) sortbuf[i] = 0ull;
-  __syncthreads();
-  bitonic_sort_desc(sortbuf, n2);
-
-  // ---- gather + decode + NMS preparation ------------------------------------------------
   const size_t o0 = (size_t)b * out.cap;
   float vmax = -CUDART_INF_F;
-  for (int i = tid; i < kk; i += kSelThreads) {
-    const unsigned long long e = sortbuf[i];
+
+  // decode one selected point: box (head.py:29-38), class, score -> candidate row i
+  auto emit = [&](const unsigned long long e, const int i) {
     const int p = (int)(0xffffffffu - (uint32_t)(e & 0xffffffffull));
     const int l = level_of_point(lt, p);
     const int pos = p - lt.point_off[l];
@@ -170,6 +172,20 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
     if (cand_point) cand_point[o0 + i] = p;
     reinterpret_cast<float4*>(out.box)[o0 + i] = bx;
     vmax = fmaxf(vmax, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+  };
+
+  __syncthreads();
+  if (n2 <= kSelThreads) {
+    // one key per thread: shuffle network inside warps, shared memory only for distances >= 32
+    unsigned long long v = (tid < kk) ? sortbuf[tid] : 0ull;
+    __syncthreads();
+    v = bitonic_sort_desc_regs(v, n2, sortbuf);
+    if (tid < kk) emit(v, tid);
+  } else {
+    for (int i = kk + tid; i < n2; i += kSelThreads) sortbuf[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc(sortbuf, n2);
+    for (int i = tid; i < kk; i += kSelThreads) emit(sortbuf[i], i);
   }
   if (out.nms_box) {
     vmax = block_max(vmax, s_fmax);
@@ -185,7 +201,8 @@ int launch_select_topk(const LevelTable& lt, int batch, const float* score, cons
   const int k = max_box < lt.num_points ? max_box : lt.num_points;
   int n2 = 1;
   while (n2 < k) n2 <<= 1;
-  const size_t smem = (size_t)n2 * sizeof(unsigned long long);
+  // sort buffer; the one-key-per-thread network needs 2 x 1024 keys of exchange scratch
+  const size_t smem = (size_t)(n2 > 2 * kSelThreads ? n2 : 2 * kSelThreads) * sizeof(unsigned long long);
   if (lt.num_points <= kSelItems * kSelThreads) {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(select_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
