@@ -41,12 +41,16 @@ assign_targets_kernel(const AssignTable at, const int M, const float* __restrict
   GtEntry* list = reinterpret_cast<GtEntry*>(smem_raw);
   __shared__ int s_n;
 
-  const int b = blockIdx.y;
+  // grid = (image, tile) with the tile order reversed: the coarse levels, whose tiles see the longest
+  // box lists, are scheduled first and consecutive CTAs (same tile, different images) cost the same,
+  // so the block scheduler spreads the expensive tiles over all SMs instead of piling them up.
+  const int b = blockIdx.x;
+  const int tile = (int)gridDim.y - 1 - (int)blockIdx.y;
   int l = 0;
 #pragma unroll
-  for (int i = 1; i < B200DET_MAX_LEVELS; ++i) l += (i < at.n_levels && (int)blockIdx.x >= at.tile_off[i]) ? 1 : 0;
+  for (int i = 1; i < B200DET_MAX_LEVELS; ++i) l += (i < at.n_levels && tile >= at.tile_off[i]) ? 1 : 0;
   const int hw = at.hw[l], w = at.w[l], s = at.stride[l];
-  const int t0 = (blockIdx.x - at.tile_off[l]) * kTile;
+  const int t0 = (tile - at.tile_off[l]) * kTile;
   const int t1 = min(t0 + kTile, hw) - 1;
   const float lo = at.lo[l], hi = at.hi[l], radius = at.radius[l];
   const int half = s / 2;
@@ -134,7 +138,7 @@ extern "C" int b200det_assign_targets(const int32_t* level_hw, const int32_t* st
                                       float* cnt_t, float* reg_t, int32_t* gt_index, void* stream) {
   using namespace b200det;
   if (!level_hw || !strides || !limit_lo || !limit_hi || !radius_px || n_levels <= 0 ||
-      n_levels > B200DET_MAX_LEVELS || batch <= 0 || batch > 65535 || max_gt < 0 || !cls_t || !cnt_t || !reg_t)
+      n_levels > B200DET_MAX_LEVELS || batch <= 0 || max_gt < 0 || !cls_t || !cnt_t || !reg_t)
     return B200DET_ERR_ARG;
   if (max_gt > 0 && (!gt_boxes || !gt_labels)) return B200DET_ERR_ARG;
   if (!aligned16(gt_boxes) || !aligned16(reg_t)) return B200DET_ERR_ARG;
@@ -163,11 +167,12 @@ extern "C" int b200det_assign_targets(const int32_t* level_hw, const int32_t* st
   at.tile_off[B200DET_MAX_LEVELS] = toff;
   at.n_levels = n_levels;
   at.num_points = (int)off;
+  if (toff > 65535) return B200DET_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(assign_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
   }
-  assign_targets_kernel<<<dim3(toff, batch), kTileThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+  assign_targets_kernel<<<dim3(batch, toff), kTileThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       at, max_gt, gt_boxes, reinterpret_cast<const long long*>(gt_labels), reinterpret_cast<long long*>(cls_t), cnt_t,
       reg_t, gt_index);
   return check_launch();

@@ -71,16 +71,19 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long* buf, int n
   }
 }
 
-// DESCENDING bitonic sort of n (power of two, <= blockDim.x) 64-bit keys held ONE PER THREAD
-// (thread t holds element t; threads >= n must pass 0 and still call).  Exchanges at distance
+// DESCENDING bitonic sort of N (power of two, <= blockDim.x) 64-bit keys held ONE PER THREAD
+// (thread t holds element t; threads >= N must pass 0 and still call).  Exchanges at distance
 // < 32 are warp shuffles (no barrier); larger distances go through `scratch` (2 * blockDim.x
-// keys, double-buffered so each such stage costs one barrier).  For n = 1024: 15 barriers instead
-// of the 55 of the all-shared-memory network.
-__device__ __forceinline__ unsigned long long bitonic_sort_desc_regs(unsigned long long v, int n,
+// keys, double-buffered so each such stage costs one barrier).  For N = 1024: 15 barriers instead
+// of the 55 of the all-shared-memory network.  Fully unrolled: every stage's masks are constants.
+template <int N>
+__device__ __forceinline__ unsigned long long bitonic_sort_desc_regs(unsigned long long v,
                                                                      unsigned long long* scratch) {
   const int t = threadIdx.x;
   int flip = 0;
-  for (int k = 2; k <= n; k <<= 1) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
       unsigned long long pv;
       if (j >= 32) {
@@ -94,9 +97,8 @@ __device__ __forceinline__ unsigned long long bitonic_sort_desc_regs(unsigned lo
         const unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), j);
         pv = ((unsigned long long)hi << 32) | lo;
       }
-      const bool desc = (t & k) == 0;
-      const bool lower = (t & j) == 0;
-      const bool take_max = (lower == desc);
+      // lower index of the pair keeps the max in a descending run, the min in an ascending one
+      const bool take_max = ((t & k) == 0) == ((t & j) == 0);
       const bool pv_gt = pv > v;
       v = (take_max == pv_gt) ? pv : v;
     }

@@ -91,7 +91,8 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- device helpers ---------------------------------------------------------------------
 // sigmoid as torch computes it: 1 / (1 + exp(-x)), IEEE division, full-precision expf.
-__device__ __forceinline__ float sigmoid_f32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+// (__frcp_rn is the correctly rounded reciprocal, i.e. bit-identical to 1.0f / y.)
+__device__ __forceinline__ float sigmoid_f32(float x) { return __frcp_rn(__fadd_rn(1.0f, expf(-x))); }
 
 // streaming (read-once) loads that do not allocate in L1
 __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {

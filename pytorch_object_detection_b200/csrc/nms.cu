@@ -85,6 +85,38 @@ nms_prepare_kernel(const int n, const float* __restrict__ boxes, const float* __
 // ------------------------------------------------------------------------------------------
 // suppression mask
 // ------------------------------------------------------------------------------------------
+// One 64-wide row of mask bits: box `a` (row) against the 64 staged column boxes.
+// Fast path per pair: 4 min/max + 2 compares.  w > 0 <=> min(x2) > max(x1) exactly in IEEE
+// arithmetic, so the reference's max(0, .) products are only formed for overlapping pairs.
+template <bool DIAG>
+__device__ __forceinline__ unsigned long long mask_row(const float4 a, const float aarea, const int acls,
+                                                       const float4* __restrict__ cbox,
+                                                       const float* __restrict__ carea,
+                                                       const int* __restrict__ ccls, const int t,
+                                                       const float thr_up, const bool zero_suppresses,
+                                                       const bool same_class_only) {
+  unsigned lo = 0u, hi = 0u;
+#pragma unroll
+  for (int j = 0; j < kNmsTile; ++j) {
+    const float4 c = cbox[j];                      // same address in every lane: broadcast
+    const float xx1 = fmaxf(a.x, c.x), yy1 = fmaxf(a.y, c.y);
+    const float xx2 = fminf(a.z, c.z), yy2 = fminf(a.w, c.w);
+    bool sup = false;
+    if (zero_suppresses || (xx2 > xx1 && yy2 > yy1)) {
+      const float w = fmaxf(0.f, __fsub_rn(xx2, xx1));
+      const float h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+      const float inter = __fmul_rn(w, h);
+      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, carea[j]), inter));
+      sup = ovr >= thr_up;                         // == (double)ovr > thr, see launch_nms
+      if (same_class_only) sup = sup && (ccls[j] == acls);
+    }
+    if (DIAG) sup = sup && (j > t);
+    if (j < 32) lo |= sup ? (1u << j) : 0u;
+    else hi |= sup ? (1u << (j - 32)) : 0u;
+  }
+  return ((unsigned long long)hi << 32) | lo;
+}
+
 __global__ void __launch_bounds__(kNmsTile)
 nms_mask_kernel(const CandSet set, const int wcap, const float thr_up, const bool zero_suppresses,
                 unsigned long long* __restrict__ mask) {
@@ -105,6 +137,12 @@ nms_mask_kernel(const CandSet set, const int wcap, const float thr_up, const boo
     cbox[t] = v;
     carea[t] = __fmul_rn(__fsub_rn(v.z, v.x), __fsub_rn(v.w, v.y));
     ccls[t] = set.cls[o0 + cj];
+  } else {
+    // beyond the image's candidates: an inverted infinite box overlaps nothing (min(x2) = -inf is never
+    // > max(x1) = +inf) and its NaN area keeps the IoU unordered on the thr < 0 path -> bit stays 0
+    cbox[t] = make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+    carea[t] = __int_as_float(0x7fc00000);
+    ccls[t] = -1;
   }
   __syncthreads();
 
@@ -113,23 +151,9 @@ nms_mask_kernel(const CandSet set, const int wcap, const float thr_up, const boo
   const float4 a = reinterpret_cast<const float4*>(set.nms_box)[o0 + i];
   const float aarea = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
   const int acls = set.cls[o0 + i];
-  const int jend = min(kNmsTile, n - cb * kNmsTile);
-  unsigned long long bits = 0ull;
-  for (int j = (cb == rb) ? t + 1 : 0; j < jend; ++j) {
-    const float4 c = cbox[j];
-    const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, c.z), fmaxf(a.x, c.x)));
-    const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, c.w), fmaxf(a.y, c.y)));
-    bool sup;
-    if (!zero_suppresses && (w <= 0.f || h <= 0.f)) {
-      sup = false;                                   // inter = 0 -> iou is 0 or NaN, never > thr >= 0
-    } else {
-      const float inter = __fmul_rn(w, h);
-      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, carea[j]), inter));
-      sup = ovr >= thr_up;                           // == (double)ovr > thr, see launch_nms
-    }
-    if (same_class_only) sup = sup && (ccls[j] == acls);
-    if (sup) bits |= 1ull << j;
-  }
+  const unsigned long long bits =
+      (cb == rb) ? mask_row<true>(a, aarea, acls, cbox, carea, ccls, t, thr_up, zero_suppresses, same_class_only)
+                 : mask_row<false>(a, aarea, acls, cbox, carea, ccls, t, thr_up, zero_suppresses, same_class_only);
   mask[(o0 + i) * wcap + cb] = bits;
 }
 
@@ -272,10 +296,14 @@ nms_scan_smem_kernel(const CandSet set, const int wcap, const unsigned long long
   const size_t q0 = (size_t)b * out.stride;
 
   // stage rows [r0, r1): row i needs the words of its own block and the blocks ahead
+  // A warp covers 32 / wp2 rows per step (wp2 = W rounded up to a power of two <= 32), one 8-byte
+  // word per lane, so the copy loop is a handful of instructions per row.
+  int wp2 = 1;
+  while (wp2 < W) wp2 <<= 1;
+  const int sub = lane / wp2, wl = lane & (wp2 - 1), rows_per_step = 32 / wp2;
   auto stage_rows = [&](int r0, int r1) {
-    for (int i = r0 + warp; i < r1; i += kWarps)
-      for (int w = (i >> 6) + lane; w < W; w += 32)
-        cp_async8(M + (size_t)i * stride + w, mask + (o0 + i) * wcap + w);
+    for (int i = r0 + warp * rows_per_step + sub; i < r1; i += kWarps * rows_per_step)
+      if (wl >= (i >> 6) && wl < W) cp_async8(M + (size_t)i * stride + wl, mask + (o0 + i) * wcap + wl);
     cp_async_commit();
   };
   const int split = min(n, 4 * kNmsTile);

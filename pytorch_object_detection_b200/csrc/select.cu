@@ -104,9 +104,11 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
   }
 
   // ---- k-th largest key -----------------------------------------------------------------
+  const int n2 = next_pow2(kk);
+  const int sort_cap = n2;    // the sort below handles up to n2 keys and orders ties by point index
   uint32_t T = kmin;          // count(key >= kmin) = n_valid
   int cntT = n_valid;
-  if (n_valid > kk) {
+  if (n_valid > sort_cap) {
     const uint32_t diff = kmin ^ kmax;              // non-zero here unless all keys are equal
     const int top = diff ? 31 - __clz(diff) : -1;
     T = (top >= 0) ? (kmax & ~((2u << top) - 1u)) : kmax;
@@ -118,13 +120,14 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
       if (c >= kk) {
         T = cand;
         cntT = c;
-        if (c == kk) break;
+        if (c <= sort_cap) break;        // everything >= T fits the sort: it finishes the selection
       }
     }
   }
-  // cntT = count(key >= T) >= kk.  If larger, T is exactly the k-th key and ties straddle it.
+  // cntT = count(key >= T) >= kk.  If it exceeds the sort capacity every bit was decided: T is
+  // exactly the k-th key and more ties sit on it than fit -> keep the lowest point indices.
   int idx_lim = 0x7fffffff;
-  if (cntT > kk) {
+  if (cntT > sort_cap) {
     int c = 0;
     FOR_KEYS(c += (kx > T) ? 1 : 0;)
     const int c_gt = block_sum(c, s_red, phase);
@@ -144,11 +147,10 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
   int mine = 0;
   FOR_KEYS(mine += (kx > T || (kx == T && ix < idx_lim)) ? 1 : 0;)
   int total;
-  int at = block_exclusive_scan(mine, s_scan, &total);    // total == kk
+  int at = block_exclusive_scan(mine, s_scan, &total);    // kk <= total <= n2
   FOR_KEYS(if (kx > T || (kx == T && ix < idx_lim)) {
     sortbuf[at++] = ((unsigned long long)kx << 32) | (unsigned long long)(0xffffffffu - (uint32_t)ix);
   })
-  const int n2 = next_pow2(kk);
   const size_t o0 = (size_t)b * out.cap;
   float vmax = -CUDART_INF_F;
 
@@ -177,12 +179,14 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
   __syncthreads();
   if (n2 <= kSelThreads) {
     // one key per thread: shuffle network inside warps, shared memory only for distances >= 32
-    unsigned long long v = (tid < kk) ? sortbuf[tid] : 0ull;
+    unsigned long long v = (tid < total) ? sortbuf[tid] : 0ull;
     __syncthreads();
-    v = bitonic_sort_desc_regs(v, n2, sortbuf);
+    if (n2 <= 64) v = bitonic_sort_desc_regs<64>(v, sortbuf);
+    else if (n2 <= 256) v = bitonic_sort_desc_regs<256>(v, sortbuf);
+    else v = bitonic_sort_desc_regs<1024>(v, sortbuf);
     if (tid < kk) emit(v, tid);
   } else {
-    for (int i = kk + tid; i < n2; i += kSelThreads) sortbuf[i] = 0ull;
+    for (int i = total + tid; i < n2; i += kSelThreads) sortbuf[i] = 0ull;
     __syncthreads();
     bitonic_sort_desc(sortbuf, n2);
     for (int i = tid; i < kk; i += kSelThreads) emit(sortbuf[i], i);
