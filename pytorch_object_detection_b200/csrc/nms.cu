@@ -85,41 +85,14 @@ nms_prepare_kernel(const int n, const float* __restrict__ boxes, const float* __
 // ------------------------------------------------------------------------------------------
 // suppression mask
 // ------------------------------------------------------------------------------------------
-// One 64-wide row of mask bits: box `a` (row) against the 64 staged column boxes.
-// Fast path per pair: 4 min/max + 2 compares.  w > 0 <=> min(x2) > max(x1) exactly in IEEE
-// arithmetic, so the reference's max(0, .) products are only formed for overlapping pairs.
-template <bool DIAG>
-__device__ __forceinline__ unsigned long long mask_row(const float4 a, const float aarea, const int acls,
-                                                       const float4* __restrict__ cbox,
-                                                       const float* __restrict__ carea,
-                                                       const int* __restrict__ ccls, const int t,
-                                                       const float thr_up, const bool zero_suppresses,
-                                                       const bool same_class_only) {
-  unsigned lo = 0u, hi = 0u;
-#pragma unroll
-  for (int j = 0; j < kNmsTile; ++j) {
-    const float4 c = cbox[j];                      // same address in every lane: broadcast
-    const float xx1 = fmaxf(a.x, c.x), yy1 = fmaxf(a.y, c.y);
-    const float xx2 = fminf(a.z, c.z), yy2 = fminf(a.w, c.w);
-    bool sup = false;
-    if (zero_suppresses || (xx2 > xx1 && yy2 > yy1)) {
-      const float w = fmaxf(0.f, __fsub_rn(xx2, xx1));
-      const float h = fmaxf(0.f, __fsub_rn(yy2, yy1));
-      const float inter = __fmul_rn(w, h);
-      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, carea[j]), inter));
-      sup = ovr >= thr_up;                         // == (double)ovr > thr, see launch_nms
-      if (same_class_only) sup = sup && (ccls[j] == acls);
-    }
-    if (DIAG) sup = sup && (j > t);
-    if (j < 32) lo |= sup ? (1u << j) : 0u;
-    else hi |= sup ? (1u << (j - 32)) : 0u;
-  }
-  return ((unsigned long long)hi << 32) | lo;
-}
-
+// One CTA of 64 threads per 64x64 tile: thread t owns row rb*64+t and walks the 64 staged column
+// boxes.  Fast path per pair: one broadcast LDS.128, 4 min/max, 2 compares.  w > 0 <=> min(x2) >
+// max(x1) exactly in IEEE arithmetic, so the reference's max(0, .) products and the division are
+// only evaluated when some lane of the warp has an overlapping pair.  ZERO_SUP (thr < 0, where a
+// zero IoU suppresses) takes the full expression for every pair.
+template <bool ZERO_SUP>
 __global__ void __launch_bounds__(kNmsTile)
-nms_mask_kernel(const CandSet set, const int wcap, const float thr_up, const bool zero_suppresses,
-                unsigned long long* __restrict__ mask) {
+nms_mask_kernel(const CandSet set, const int wcap, const float thr_up, unsigned long long* __restrict__ mask) {
   const int cb = blockIdx.x, rb = blockIdx.y, b = blockIdx.z;
   if (cb < rb) return;
   const int n = set.count[b];
@@ -147,14 +120,38 @@ nms_mask_kernel(const CandSet set, const int wcap, const float thr_up, const boo
   __syncthreads();
 
   const int i = rb * kNmsTile + t;
-  if (i >= n) return;
-  const float4 a = reinterpret_cast<const float4*>(set.nms_box)[o0 + i];
+  const bool row_ok = i < n;                       // keep whole warps in the loop (warp votes below)
+  const float4 a = row_ok ? reinterpret_cast<const float4*>(set.nms_box)[o0 + i]
+                          : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
   const float aarea = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
-  const int acls = set.cls[o0 + i];
-  const unsigned long long bits =
-      (cb == rb) ? mask_row<true>(a, aarea, acls, cbox, carea, ccls, t, thr_up, zero_suppresses, same_class_only)
-                 : mask_row<false>(a, aarea, acls, cbox, carea, ccls, t, thr_up, zero_suppresses, same_class_only);
-  mask[(o0 + i) * wcap + cb] = bits;
+  const int acls = row_ok ? set.cls[o0 + i] : -2;
+  // pass 1 (branch-free, fully unrolled): candidate bit j <=> the boxes overlap with positive area
+  const unsigned cbase = (unsigned)__cvta_generic_to_shared(cbox);
+  unsigned lo = 0u, hi = 0u;
+#pragma unroll
+  for (int j = 0; j < kNmsTile; ++j) {
+    float4 c;                                       // same address in every lane: broadcast LDS.128
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "r"(cbase + j * 16));
+    const bool overlap = ZERO_SUP || (fminf(a.z, c.z) > fmaxf(a.x, c.x) && fminf(a.w, c.w) > fmaxf(a.y, c.y));
+    if (j < 32) lo |= overlap ? (1u << j) : 0u;
+    else hi |= overlap ? (1u << (j - 32)) : 0u;
+  }
+  unsigned long long bits = ((unsigned long long)hi << 32) | lo;
+  // pass 2 (rare): the reference's exact IoU expression for the candidates only
+  for (unsigned long long m = bits; m; m &= m - 1ull) {
+    const int j = __ffsll((long long)m) - 1;
+    const float4 c = cbox[j];
+    const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, c.z), fmaxf(a.x, c.x)));
+    const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, c.w), fmaxf(a.y, c.y)));
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, carea[j]), inter));
+    bool sup = ovr >= thr_up;                        // == (double)ovr > thr, see launch_nms
+    if (same_class_only) sup = sup && (ccls[j] == acls);
+    if (!sup) bits &= ~(1ull << j);
+  }
+  if (cb == rb) bits &= ~((2ull << t) - 1ull);     // diagonal tile: only later boxes (j > t)
+  if (row_ok) mask[(o0 + i) * wcap + cb] = bits;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -440,7 +437,10 @@ int launch_nms(const CandSet& set, int batch, double nms_thr, int clip_h, int cl
   if (!((double)thr_up > nms_thr)) thr_up = nextafterf(thr_up, INFINITY);
   const bool zero_suppresses = !(nms_thr >= 0.0);
   const int wblocks = (set.cap + kNmsTile - 1) / kNmsTile;
-  nms_mask_kernel<<<dim3(wblocks, wblocks, batch), kNmsTile, 0, stream>>>(set, wcap, thr_up, zero_suppresses, mask);
+  if (zero_suppresses)
+    nms_mask_kernel<true><<<dim3(wblocks, wblocks, batch), kNmsTile, 0, stream>>>(set, wcap, thr_up, mask);
+  else
+    nms_mask_kernel<false><<<dim3(wblocks, wblocks, batch), kNmsTile, 0, stream>>>(set, wcap, thr_up, mask);
   int rc = check_launch();
   if (rc) return rc;
   if (set.cap <= kSmemScanMaxCap) {
