@@ -43,7 +43,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    trace = ["-DB200DET_TRACE"] if os.environ.get("B200DET_TRACE") == "1" else []   # phase timestamps (debug)
+    cmd = [_nvcc()] + NVCC_FLAGS + trace + (["-Xptxas", "-v"] if verbose else []) + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -1,6 +1,6 @@
 // K4a — FCOS target assignment (FCOSGenTargets.generate_target, model/modules/head.py:235-316).
 //
-// The reference materialises [B, HW, M, 4] offsets and reduces over M.  Here a CTA owns 512
+// The reference materialises [B, HW, M, 4] offsets and reduces over M.  Here a CTA owns 2048
 // consecutive points of one level of one image.  The centre-sampling mask
 // (max(|x-cx|, |y-cy|) < 1.5*stride, head.py:275-283) means only ground-truth boxes whose centre
 // row lies within 1.5 strides of the tile's rows can be positive for it, so the CTA first
@@ -26,14 +26,18 @@ struct AssignTable {
   int n_levels, num_points;
 };
 
+constexpr int kAssignThreads = 256;
+constexpr int kAssignPts = 8;
+constexpr int kAssignTile = kAssignThreads * kAssignPts;   // 2048 points of one level of one image per CTA
+
 struct GtEntry {
   float x0, y0, x1, y1;
   float cx, cy;          // (x0+x1)/2, (y0+y1)/2 as the reference rounds them (head.py:276-277)
   int idx;
-  int pad_;
+  int label;             // class label (fits int32), staged so the epilogue has no dependent global load
 };
 
-__global__ void __launch_bounds__(kTileThreads, 4)
+__global__ void __launch_bounds__(kAssignThreads, 2)
 assign_targets_kernel(const AssignTable at, const int M, const float* __restrict__ gt_boxes,
                       const long long* __restrict__ gt_labels, long long* __restrict__ cls_t,
                       float* __restrict__ cnt_t, float* __restrict__ reg_t, int32_t* __restrict__ gt_index) {
@@ -50,8 +54,8 @@ assign_targets_kernel(const AssignTable at, const int M, const float* __restrict
 #pragma unroll
   for (int i = 1; i < B200DET_MAX_LEVELS; ++i) l += (i < at.n_levels && tile >= at.tile_off[i]) ? 1 : 0;
   const int hw = at.hw[l], w = at.w[l], s = at.stride[l];
-  const int t0 = (tile - at.tile_off[l]) * kTile;
-  const int t1 = min(t0 + kTile, hw) - 1;
+  const int t0 = (tile - at.tile_off[l]) * kAssignTile;
+  const int t1 = min(t0 + kAssignTile, hw) - 1;
   const float lo = at.lo[l], hi = at.hi[l], radius = at.radius[l];
   const int half = s / 2;
 
@@ -65,14 +69,17 @@ assign_targets_kernel(const AssignTable at, const int M, const float* __restrict
     const float ymin = (float)((t0 / w) * s + half) - radius - 1.0f;
     const float ymax = (float)((t1 / w) * s + half) + radius + 1.0f;
     const float4* g4 = reinterpret_cast<const float4*>(gt_boxes) + (size_t)b * M;
-    for (int m = threadIdx.x; m < M; m += kTileThreads) {
+    const long long* lab = gt_labels + (size_t)b * M;
+    for (int m = threadIdx.x; m < M; m += kAssignThreads) {
       const float4 g = g4[m];
+      const int label = (int)lab[m];
       const float cx = __fmul_rn(__fadd_rn(g.x, g.z), 0.5f);
       const float cy = __fmul_rn(__fadd_rn(g.y, g.w), 0.5f);
       const float side = fmaxf(g.z - g.x, g.w - g.y);
-      if (cy >= ymin && cy <= ymax && side > lo - 1.0f && 0.5f * side <= hi + 1.0f) {
+      // side > 0 drops the -1 padding rows (and degenerate boxes): a point cannot be strictly inside them
+      if (cy >= ymin && cy <= ymax && side > 0.f && side > lo - 1.0f && 0.5f * side <= hi + 1.0f) {
         const int at_ = atomicAdd(&s_n, 1);
-        list[at_] = GtEntry{g.x, g.y, g.z, g.w, cx, cy, m, 0};
+        list[at_] = GtEntry{g.x, g.y, g.z, g.w, cx, cy, m, label};
       }
     }
   }
@@ -81,9 +88,9 @@ assign_targets_kernel(const AssignTable at, const int M, const float* __restrict
 
   const size_t out0 = (size_t)b * at.num_points + at.point_off[l];
   const float inv_w = 1.0f / (float)w;
-#pragma unroll
-  for (int q = 0; q < kTilePts; ++q) {
-    const int pos = t0 + threadIdx.x + q * kTileThreads;    // strided: every store instruction is coalesced
+#pragma unroll 2
+  for (int q = 0; q < kAssignPts; ++q) {
+    const int pos = t0 + threadIdx.x + q * kAssignThreads;  // strided: every store instruction is coalesced
     if (pos >= hw) break;
     int row = (int)((float)pos * inv_w);                    // estimate within +-1, then fix up exactly
     int col = pos - row * w;
@@ -92,7 +99,7 @@ assign_targets_kernel(const AssignTable at, const int M, const float* __restrict
     const float x = (float)(col * s + half);
     const float y = (float)(row * s + half);
     float best_area = CUDART_INF_F;
-    int best_m = -1;
+    int best_m = -1, best_label = 0;
     float bl = -1.f, bt = -1.f, br = -1.f, bb = -1.f;
     for (int e = 0; e < n_list; ++e) {
       const GtEntry g = list[e];
@@ -109,6 +116,7 @@ assign_targets_kernel(const AssignTable at, const int M, const float* __restrict
         if (area < best_area || (area == best_area && g.idx < best_m)) {
           best_area = area;
           best_m = g.idx;
+          best_label = g.label;
           bl = lf; bt = tf; br = rf; bb = bf;
         }
       }
@@ -116,7 +124,7 @@ assign_targets_kernel(const AssignTable at, const int M, const float* __restrict
     long long label = 0;
     float cnt = -1.f;
     if (best_m >= 0) {
-      label = gt_labels[(size_t)b * M + best_m];
+      label = (long long)best_label;
       const float lr_min = fminf(bl, br), lr_max = fmaxf(bl, br);
       const float tb_min = fminf(bt, bb), tb_max = fmaxf(bt, bb);
       cnt = __fsqrt_rn(__fdiv_rn(__fmul_rn(lr_min, tb_min), __fadd_rn(__fmul_rn(lr_max, tb_max), 1e-10f)));
@@ -160,7 +168,7 @@ extern "C" int b200det_assign_targets(const int32_t* level_hw, const int32_t* st
     at.point_off[l] = (int)off;
     at.tile_off[l] = toff;
     off += at.hw[l];
-    toff += (at.hw[l] + kTile - 1) / kTile;
+    toff += (at.hw[l] + kAssignTile - 1) / kAssignTile;
     if (off > (1ll << 30)) return B200DET_ERR_ARG;
   }
   at.point_off[B200DET_MAX_LEVELS] = (int)off;
@@ -172,7 +180,7 @@ extern "C" int b200det_assign_targets(const int32_t* level_hw, const int32_t* st
     cudaError_t e = cudaFuncSetAttribute(assign_targets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
   }
-  assign_targets_kernel<<<dim3(batch, toff), kTileThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+  assign_targets_kernel<<<dim3(batch, toff), kAssignThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       at, max_gt, gt_boxes, reinterpret_cast<const long long*>(gt_labels), reinterpret_cast<long long*>(cls_t), cnt_t,
       reg_t, gt_index);
   return check_launch();

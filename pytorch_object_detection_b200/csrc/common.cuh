@@ -89,6 +89,28 @@ inline int check_launch() {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ---- optional phase tracing (build with -DB200DET_TRACE; scripts/trace_phases.py reads it) --------
+#ifdef B200DET_TRACE
+#define B200DET_TRACE_BUFFER(name)                                                   \
+  namespace b200det { static __device__ long long g_trace[64]; }                     \
+  extern "C" int b200det_debug_read_trace_##name(long long* host_out, int n) {       \
+    return (int)cudaMemcpyFromSymbol(host_out, b200det::g_trace, sizeof(long long) * (n > 64 ? 64 : n)); \
+  }
+#define B200DET_STAMP(slot)                                                          \
+  do {                                                                               \
+    __syncthreads();                                                                 \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_trace[slot] = clock64(); \
+  } while (0)
+#define B200DET_STAMP_NOSYNC(slot)                                                   \
+  do {                                                                               \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_trace[slot] = clock64(); \
+  } while (0)
+#else
+#define B200DET_TRACE_BUFFER(name)
+#define B200DET_STAMP(slot) do {} while (0)
+#define B200DET_STAMP_NOSYNC(slot) do {} while (0)
+#endif
+
 // ---- device helpers ---------------------------------------------------------------------
 // sigmoid as torch computes it: 1 / (1 + exp(-x)), IEEE division, full-precision expf.
 // (__frcp_rn is the correctly rounded reciprocal, i.e. bit-identical to 1.0f / y.)

@@ -16,6 +16,8 @@
 #include "block_utils.cuh"
 #include "nms.cuh"
 
+B200DET_TRACE_BUFFER(nms)
+
 #include <math.h>
 
 namespace b200det {
@@ -284,6 +286,7 @@ nms_scan_smem_kernel(const CandSet set, const int wcap, const unsigned long long
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kSmemScanThreads / 32;
   const int b = blockIdx.x;
+  B200DET_STAMP_NOSYNC(16);
   const int n = set.count[b];
   const int W = (n + kNmsTile - 1) / kNmsTile;              // <= 20
   const int stride = wcap | 1;
@@ -309,6 +312,7 @@ nms_scan_smem_kernel(const CandSet set, const int wcap, const unsigned long long
   if (tid < 32) keepw[tid] = 0ull;
   cp_async_wait<1>();
   __syncthreads();                                           // rows [0, split) resident
+  B200DET_STAMP_NOSYNC(17);
 
   if (warp != 0) {
     cp_async_wait<0>();
@@ -359,6 +363,7 @@ nms_scan_smem_kernel(const CandSet set, const int wcap, const unsigned long long
   }
   __syncthreads();
 
+  B200DET_STAMP_NOSYNC(18);
   if (warp == 0) {                                           // exclusive prefix of kept counts per block
     const int cnt = (lane < W) ? __popcll(keepw[lane]) : 0;
     int incl = cnt;
@@ -371,22 +376,44 @@ nms_scan_smem_kernel(const CandSet set, const int wcap, const unsigned long long
     if (lane == 31) s_pre[32] = incl;
   }
   __syncthreads();
-  for (int q = tid; q < n; q += kSmemScanThreads) {
-    const unsigned long long kw = keepw[q >> 6];
-    if (!((kw >> (q & 63)) & 1ull)) continue;
-    const int o = s_pre[q >> 6] + __popcll(kw & ((1ull << (q & 63)) - 1ull));
-    float4 bx = reinterpret_cast<const float4*>(set.box)[o0 + q];
-    if (clip_h > 0) {   // ClipBoxes: clamp_(min=0), then x <= w-1, y <= h-1   (head.py:156-162)
-      bx.x = clip1(bx.x, (float)(clip_w - 1));
-      bx.y = clip1(bx.y, (float)(clip_h - 1));
-      bx.z = clip1(bx.z, (float)(clip_w - 1));
-      bx.w = clip1(bx.w, (float)(clip_h - 1));
+  // kept boxes in keep order; the gathers of all of a thread's rows are issued before any store
+  constexpr int kRowsPerThread = (kSmemScanMaxCap + kSmemScanThreads - 1) / kSmemScanThreads;
+  int oidx[kRowsPerThread];
+  float4 bx[kRowsPerThread];
+  float sc[kRowsPerThread];
+  int cl[kRowsPerThread], sr[kRowsPerThread];
+#pragma unroll
+  for (int u = 0; u < kRowsPerThread; ++u) {
+    const int q = tid + u * kSmemScanThreads;
+    oidx[u] = -1;
+    if (q < n) {
+      const unsigned long long kw = keepw[q >> 6];
+      if ((kw >> (q & 63)) & 1ull) {
+        oidx[u] = s_pre[q >> 6] + __popcll(kw & ((1ull << (q & 63)) - 1ull));
+        bx[u] = reinterpret_cast<const float4*>(set.box)[o0 + q];
+        sc[u] = set.score[o0 + q];
+        cl[u] = set.cls[o0 + q];
+        sr[u] = set.src[o0 + q];
+      }
     }
-    out.score[q0 + o] = set.score[o0 + q];
-    out.cls[q0 + o] = (long long)set.cls[o0 + q];
-    out.keep[q0 + o] = (long long)set.src[o0 + q];
-    reinterpret_cast<float4*>(out.box)[q0 + o] = bx;
   }
+#pragma unroll
+  for (int u = 0; u < kRowsPerThread; ++u) {
+    if (oidx[u] < 0) continue;
+    float4 v = bx[u];
+    if (clip_h > 0) {   // ClipBoxes: clamp_(min=0), then x <= w-1, y <= h-1   (head.py:156-162)
+      v.x = clip1(v.x, (float)(clip_w - 1));
+      v.y = clip1(v.y, (float)(clip_h - 1));
+      v.z = clip1(v.z, (float)(clip_w - 1));
+      v.w = clip1(v.w, (float)(clip_h - 1));
+    }
+    const size_t o = q0 + oidx[u];
+    out.score[o] = sc[u];
+    out.cls[o] = (long long)cl[u];
+    out.keep[o] = (long long)sr[u];
+    reinterpret_cast<float4*>(out.box)[o] = v;
+  }
+  B200DET_STAMP(19);
   if (tid == 0) out.count[b] = s_pre[32];
 }
 

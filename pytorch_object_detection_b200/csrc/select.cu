@@ -17,11 +17,14 @@
 #include "block_utils.cuh"
 #include "nms.cuh"
 
+B200DET_TRACE_BUFFER(select)
+
 namespace b200det {
 namespace {
 
 constexpr int kSelThreads = 1024;
 constexpr int kSelItems = 24;            // register-resident keys per thread: P <= 24576
+constexpr int kFinishMax = 512;          // undecided keys handed to the single-warp finishing phase
 
 __device__ __forceinline__ uint32_t load_key(const float* sc, int i, float thr) {
   const float s = sc[i];
@@ -71,6 +74,7 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
   const float* sc = score + (size_t)b * P;
   int phase = 0;
 
+  B200DET_STAMP_NOSYNC(0);
   uint32_t key[REG ? kSelItems : 1];
   int nv = 0;
   uint32_t kmin = 0xffffffffu, kmax = 0u;
@@ -97,6 +101,7 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
   kmin = __reduce_min_sync(0xffffffffu, s_mm[lane]);
   kmax = __reduce_max_sync(0xffffffffu, s_mm[32 + lane]);
 
+  B200DET_STAMP(1);
   const int kk = min(min(max_box, P), n_valid);
   if (kk == 0) {
     if (tid == 0) { out.count[b] = 0; out.mode[b] = 0; }
@@ -112,7 +117,11 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
     const uint32_t diff = kmin ^ kmax;              // non-zero here unless all keys are equal
     const int top = diff ? 31 - __clz(diff) : -1;
     T = (top >= 0) ? (kmax & ~((2u << top) - 1u)) : kmax;
-    for (int bit = top; bit >= 0; --bit) {
+    // Phase A: block-wide passes over all keys.  `above` = count(key >= T + 2^(bit+1)) are already
+    // known to be selected; the cntT - above keys inside [T, T + 2^(bit+1)) are still undecided.
+    int above = 0, bit = top;
+    bool done = false;
+    for (; bit >= 0 && cntT - above > kFinishMax; --bit) {
       const uint32_t cand = T | (1u << bit);
       int c = 0;
       FOR_KEYS(c += (kx >= cand) ? 1 : 0;)
@@ -120,10 +129,48 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
       if (c >= kk) {
         T = cand;
         cntT = c;
-        if (c <= sort_cap) break;        // everything >= T fits the sort: it finishes the selection
+        if (c <= sort_cap) { done = true; break; }  // everything >= T fits the sort: it finishes the selection
+      } else {
+        above = c;
       }
     }
+    B200DET_STAMP(2);
+    // Phase B: the few undecided keys go to shared memory and ONE warp decides the remaining bits
+    // with warp reductions only (no block barrier per bit).
+    if (!done && bit >= 0) {
+      const uint32_t span_hi = (bit >= 31) ? 0u : (T >> (bit + 1));       // keys sharing T's bits above `bit`
+      int mine_u = 0;
+      FOR_KEYS(mine_u += (kx >= T && ((bit >= 31) || (kx >> (bit + 1)) == span_hi)) ? 1 : 0;)
+      int n_u;
+      int at_u = block_exclusive_scan(mine_u, s_scan, &n_u);              // n_u == cntT - above <= kFinishMax
+      uint32_t* ulist = reinterpret_cast<uint32_t*>(sortbuf);
+      FOR_KEYS(if (kx >= T && ((bit >= 31) || (kx >> (bit + 1)) == span_hi)) ulist[at_u++] = kx;)
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t uk[kFinishMax / 32];
+#pragma unroll
+        for (int j = 0; j < kFinishMax / 32; ++j) uk[j] = (lane + 32 * j < n_u) ? ulist[lane + 32 * j] : 0u;
+        for (; bit >= 0; --bit) {
+          const uint32_t cand = T | (1u << bit);
+          int c = 0;
+#pragma unroll
+          for (int j = 0; j < kFinishMax / 32; ++j) c += (uk[j] >= cand) ? 1 : 0;
+          c = above + __reduce_add_sync(0xffffffffu, c);   // `above` stays fixed: every key outside the list
+          if (c >= kk) {
+            T = cand;
+            cntT = c;
+            if (c <= sort_cap) break;
+          }
+        }
+        if (lane == 0) { s_mm[0] = T; s_mm[1] = (uint32_t)cntT; }
+      }
+      __syncthreads();
+      T = s_mm[0];
+      cntT = (int)s_mm[1];
+      __syncthreads();                                                    // ulist (sortbuf) is reused below
+    }
   }
+  B200DET_STAMP(3);
   // cntT = count(key >= T) >= kk.  If it exceeds the sort capacity every bit was decided: T is
   // exactly the k-th key and more ties sit on it than fit -> keep the lowest point indices.
   int idx_lim = 0x7fffffff;
@@ -151,6 +198,7 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
   FOR_KEYS(if (kx > T || (kx == T && ix < idx_lim)) {
     sortbuf[at++] = ((unsigned long long)kx << 32) | (unsigned long long)(0xffffffffu - (uint32_t)ix);
   })
+  B200DET_STAMP(4);
   const size_t o0 = (size_t)b * out.cap;
   float vmax = -CUDART_INF_F;
 
@@ -184,6 +232,7 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
     if (n2 <= 64) v = bitonic_sort_desc_regs<64>(v, sortbuf);
     else if (n2 <= 256) v = bitonic_sort_desc_regs<256>(v, sortbuf);
     else v = bitonic_sort_desc_regs<1024>(v, sortbuf);
+    B200DET_STAMP(5);
     if (tid < kk) emit(v, tid);
   } else {
     for (int i = total + tid; i < n2; i += kSelThreads) sortbuf[i] = 0ull;
@@ -191,10 +240,12 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
     bitonic_sort_desc(sortbuf, n2);
     for (int i = tid; i < kk; i += kSelThreads) emit(sortbuf[i], i);
   }
+  B200DET_STAMP(6);
   if (out.nms_box) {
     vmax = block_max(vmax, s_fmax);
     nms_prepare_boxes(out, b, kk, vmax, tid, kSelThreads);
   }
+  B200DET_STAMP(7);
   if (tid == 0) out.count[b] = kk;
 }
 
