@@ -4,17 +4,20 @@
 //   nms_prepare_kernel  (stand-alone entry only; K2 does this for the fused path)
 //       score >= thr compaction (order kept), stable descending sort, class-offset boxes.
 //   nms_mask_kernel     one CTA of 64 threads per 64x64 tile of the upper triangle: bit j of
-//       word (i, cb) says "box i suppresses box cb*64+j".  IoU in the reference's operation
+//       word (cb, i) says "box i suppresses box cb*64+j".  IoU in the reference's operation
 //       order with explicitly rounded fp32 intrinsics (no FMA contraction is possible):
 //         inter = max(0, min(x2)-max(x1)) * max(0, min(y2)-max(y1))
 //         iou   = inter / (area_i + area_j - inter),  suppressed iff (double)iou > thr.
-//   nms_scan_kernel     one CTA per image: greedy pass over the mask, 64 rows at a time staged
-//       into shared memory with cp.async (double-buffered); warp 0 resolves the 64x64 diagonal
-//       serially, all warps OR the kept rows into the removed-bitmap, and the kept boxes are
-//       written (clipped when asked) in keep order.
+//       The mask is stored COLUMN-BLOCK major, maskT[b][cb][i]: a tile's 64 words are one
+//       contiguous 512-byte store, and the scan reads 64 rows of a column as consecutive words.
+//   nms_scan_*_kernel   one CTA per image: the greedy pass.  Mask columns are brought into shared
+//       memory by the bulk-copy engine (cp.async.bulk + mbarrier transaction counts); one warp
+//       runs the dependency chain with lane = row, warp OR-reductions and the removed-bitmap in
+//       registers / shared memory; kept boxes are written (clipped when asked) in keep order.
 // This stage is latency-bound (the greedy dependency chain), not bandwidth-bound.
 #include "block_utils.cuh"
 #include "nms.cuh"
+#include "tma.cuh"
 
 B200DET_TRACE_BUFFER(nms)
 
@@ -24,7 +27,6 @@ namespace b200det {
 namespace {
 
 constexpr int kPrepThreads = 1024;
-constexpr int kScanThreads = 256;
 
 // ------------------------------------------------------------------------------------------
 // prepare (stand-alone batched_nms entry)
@@ -88,13 +90,14 @@ nms_prepare_kernel(const int n, const float* __restrict__ boxes, const float* __
 // suppression mask
 // ------------------------------------------------------------------------------------------
 // One CTA of 64 threads per 64x64 tile: thread t owns row rb*64+t and walks the 64 staged column
-// boxes.  Fast path per pair: one broadcast LDS.128, 4 min/max, 2 compares.  w > 0 <=> min(x2) >
-// max(x1) exactly in IEEE arithmetic, so the reference's max(0, .) products and the division are
-// only evaluated when some lane of the warp has an overlapping pair.  ZERO_SUP (thr < 0, where a
-// zero IoU suppresses) takes the full expression for every pair.
+// boxes.  Pass 1 is branch-free and fully unrolled (one broadcast LDS.128, 4 min/max, 2 compares
+// per pair): w > 0 <=> min(x2) > max(x1) exactly in IEEE arithmetic, so only overlapping pairs
+// become candidates.  Pass 2 evaluates the reference's exact IoU expression for the candidates.
+// ZERO_SUP (thr < 0, where a zero IoU suppresses) makes every pair a candidate.
 template <bool ZERO_SUP>
 __global__ void __launch_bounds__(kNmsTile)
-nms_mask_kernel(const CandSet set, const int wcap, const float thr_up, unsigned long long* __restrict__ mask) {
+nms_mask_kernel(const CandSet set, const int wblocks, const int cap_pad, const float thr_up,
+                unsigned long long* __restrict__ maskT) {
   const int cb = blockIdx.x, rb = blockIdx.y, b = blockIdx.z;
   if (cb < rb) return;
   const int n = set.count[b];
@@ -122,12 +125,12 @@ nms_mask_kernel(const CandSet set, const int wcap, const float thr_up, unsigned 
   __syncthreads();
 
   const int i = rb * kNmsTile + t;
-  const bool row_ok = i < n;                       // keep whole warps in the loop (warp votes below)
+  const bool row_ok = i < n;
   const float4 a = row_ok ? reinterpret_cast<const float4*>(set.nms_box)[o0 + i]
                           : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
   const float aarea = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
   const int acls = row_ok ? set.cls[o0 + i] : -2;
-  // pass 1 (branch-free, fully unrolled): candidate bit j <=> the boxes overlap with positive area
+  // pass 1: candidate bit j <=> the boxes overlap with positive area
   const unsigned cbase = (unsigned)__cvta_generic_to_shared(cbox);
   unsigned lo = 0u, hi = 0u;
 #pragma unroll
@@ -153,120 +156,15 @@ nms_mask_kernel(const CandSet set, const int wcap, const float thr_up, unsigned 
     if (!sup) bits &= ~(1ull << j);
   }
   if (cb == rb) bits &= ~((2ull << t) - 1ull);     // diagonal tile: only later boxes (j > t)
-  if (row_ok) mask[(o0 + i) * wcap + cb] = bits;
+  if (!row_ok) bits = 0ull;
+  maskT[((size_t)b * wblocks + cb) * cap_pad + i] = bits;   // 64 consecutive words per tile
 }
 
 // ------------------------------------------------------------------------------------------
-// greedy scan + output
+// greedy pass + output
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 __device__ __forceinline__ float clip1(float v, float hi) { return fminf(fmaxf(v, 0.f), hi); }
 
-__global__ void __launch_bounds__(kScanThreads)
-nms_scan_kernel(const CandSet set, const int wcap, const unsigned long long* __restrict__ mask,
-                const int clip_h, const int clip_w, const NmsOut out) {
-  extern __shared__ __align__(16) unsigned long long sm[];   // [2][64*wcap] row chunks, [wcap] removed
-  __shared__ unsigned long long s_keep;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x;
-  const int n = set.count[b];
-  const int W = (n + kNmsTile - 1) / kNmsTile;
-  const int Wr2 = ((W + 1) & ~1) / 2;                        // 16-byte units per row to stage
-  unsigned long long* removed = sm + 2 * kNmsTile * wcap;
-  const size_t o0 = (size_t)b * set.cap;
-  const size_t q0 = (size_t)b * out.stride;
-
-  for (int w = tid; w < wcap; w += kScanThreads) removed[w] = 0ull;
-
-  auto stage = [&](int rb) {
-    unsigned long long* dst = sm + (rb & 1) * kNmsTile * wcap;
-    const int rows = min(kNmsTile, n - rb * kNmsTile);
-    for (int e = tid; e < rows * Wr2; e += kScanThreads) {
-      const int r = e / Wr2, c = e - r * Wr2;
-      cp_async16(dst + r * wcap + 2 * c, mask + (o0 + rb * kNmsTile + r) * wcap + 2 * c);
-    }
-    cp_async_commit();
-  };
-
-  int total = 0;
-  if (W > 0) stage(0);
-  for (int rb = 0; rb < W; ++rb) {
-    if (rb + 1 < W) {
-      stage(rb + 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();                                         // chunk rb (and removed[]) visible
-    const unsigned long long* chunk = sm + (rb & 1) * kNmsTile * wcap;
-    const int rows = min(kNmsTile, n - rb * kNmsTile);
-    if (warp == 0) {
-      unsigned long long cur = removed[rb], keep = 0ull;
-#pragma unroll 16
-      for (int i = 0; i < kNmsTile; ++i) {
-        const unsigned long long d = chunk[i * wcap + rb];   // broadcast read, off the dependency chain
-        const bool alive = (i < rows) && !((cur >> i) & 1ull);
-        keep |= alive ? (1ull << i) : 0ull;
-        cur |= alive ? d : 0ull;
-      }
-      if (lane == 0) s_keep = keep;
-    }
-    __syncthreads();
-    const unsigned long long keep = s_keep;
-    // removed[w] |= OR of the kept rows, for the column blocks still ahead
-    for (int w = rb + 1 + lane; w < W; w += 32) {
-      unsigned long long acc = 0ull;
-      for (int i = warp; i < rows; i += kScanThreads / 32)
-        if ((keep >> i) & 1ull) acc |= chunk[i * wcap + w];
-      if (acc) atomicOr(&removed[w], acc);
-    }
-    // kept boxes of this block, in order
-    if (tid < kNmsTile && ((keep >> tid) & 1ull)) {
-      const int q = rb * kNmsTile + tid;
-      const int o = total + __popcll(keep & ((1ull << tid) - 1ull));
-      float4 bx = reinterpret_cast<const float4*>(set.box)[o0 + q];
-      if (clip_h > 0) {   // ClipBoxes: clamp_(min=0), then x <= w-1, y <= h-1   (head.py:156-162)
-        bx.x = clip1(bx.x, (float)(clip_w - 1));
-        bx.y = clip1(bx.y, (float)(clip_h - 1));
-        bx.z = clip1(bx.z, (float)(clip_w - 1));
-        bx.w = clip1(bx.w, (float)(clip_h - 1));
-      }
-      out.score[q0 + o] = set.score[o0 + q];
-      out.cls[q0 + o] = (long long)set.cls[o0 + q];
-      out.keep[q0 + o] = (long long)set.src[o0 + q];
-      reinterpret_cast<float4*>(out.box)[q0 + o] = bx;
-    }
-    total += __popcll(keep);
-    __syncthreads();                                         // removed[] complete; chunk buffer reusable
-  }
-  if (tid == 0) out.count[b] = total;
-}
-
-// ---- small-n variant: the image's whole upper-triangular mask resident in shared memory ------
-// (cap <= kSmemScanMaxCap, i.e. every reference configuration with max_detection_box = 1000).
-// All warps stage the rows with cp.async into a padded layout (odd row stride: a lane-per-row
-// column read is bank-conflict-free); then ONE warp runs the greedy pass with no block barrier
-// on its critical path:
-//   per 64-row block: lane i holds diagonal words of rows i and i+32.  If no still-alive row
-//   suppresses another still-alive row of the block (one warp OR-reduction) every alive row is
-//   kept at once; otherwise the 64 rows are resolved serially out of registers (shuffles).
-//   The kept rows are then OR-reduced column by column into the removed-bitmap, which lives in
-//   registers (lane w owns word w).
-constexpr int kSmemScanThreads = 256;
-constexpr int kSmemScanMaxCap = 1280;    // 1280 * 21 * 8 B = 210 KB
-
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
-}
 __device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
   const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
   const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
@@ -278,93 +176,122 @@ __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int s
   return ((unsigned long long)hi << 32) | lo;
 }
 
+// Resolve one 64-row block given the already-removed bits `cur` and the block's diagonal words
+// held lane-per-row (d0: row lane, d1: row lane+32).  If no still-alive row suppresses another
+// still-alive row (one warp OR-reduction) all alive rows are kept at once; otherwise the 64 rows
+// are walked serially out of registers (shuffles), the greedy rule of torchvision's nms kernel.
+__device__ __forceinline__ unsigned long long resolve_block(const unsigned long long cur, const unsigned long long valid,
+                                                            const unsigned long long d0, const unsigned long long d1,
+                                                            const int lane) {
+  const bool a0 = !((cur >> lane) & 1ull), a1 = !((cur >> (lane + 32)) & 1ull);
+  const unsigned long long S = warp_or64((a0 ? d0 : 0ull) | (a1 ? d1 : 0ull));
+  if (((S & ~cur) & valid) == 0ull) return ~cur & valid;
+  unsigned long long c = cur, keep = 0ull;
+#pragma unroll 8
+  for (int i = 0; i < kNmsTile; ++i) {
+    const unsigned long long di = shfl64(i < 32 ? d0 : d1, i & 31);
+    const bool alive = ((valid >> i) & 1ull) && !((c >> i) & 1ull);
+    keep |= alive ? (1ull << i) : 0ull;
+    c |= alive ? di : 0ull;
+  }
+  return keep;
+}
+
+// gather + (optional) clip + store of one kept row
+__device__ __forceinline__ void store_kept(const CandSet& set, const NmsOut& out, const size_t o0, const size_t q0,
+                                           const int q, const int o, const int clip_h, const int clip_w,
+                                           const float4 bx, const float sc, const int cl, const int sr) {
+  float4 v = bx;
+  if (clip_h > 0) {   // ClipBoxes: clamp_(min=0), then x <= w-1, y <= h-1   (head.py:156-162)
+    v.x = clip1(v.x, (float)(clip_w - 1));
+    v.y = clip1(v.y, (float)(clip_h - 1));
+    v.z = clip1(v.z, (float)(clip_w - 1));
+    v.w = clip1(v.w, (float)(clip_h - 1));
+  }
+  out.score[q0 + o] = sc;
+  out.cls[q0 + o] = (long long)cl;
+  out.keep[q0 + o] = (long long)sr;
+  reinterpret_cast<float4*>(out.box)[q0 + o] = v;
+}
+
+// ---- small-n variant: the image's whole upper-triangular mask resident in shared memory ------
+// cap <= kSmemScanMaxCap (every reference configuration: max_detection_box = 1000).  Column block w
+// holds the words of rows [0, (w+1)*64); thread 0 issues one bulk copy per column block, all of
+// them completing on one mbarrier.  All warps then flag, per (row block, column block), whether
+// any word is non-zero; warp 0 runs the greedy pass touching only flagged pairs.
+constexpr int kSmemScanThreads = 256;
+constexpr int kSmemScanMaxBlocks = 28;                       // 28*29/2 * 512 B = 203 KB
+constexpr int kSmemScanMaxCap = kSmemScanMaxBlocks * kNmsTile;   // 1792
+
+__device__ __forceinline__ int col_off(int w) { return kNmsTile * (w * (w + 1) / 2); }   // words before column w
+
 __global__ void __launch_bounds__(kSmemScanThreads, 1)
-nms_scan_smem_kernel(const CandSet set, const int wcap, const unsigned long long* __restrict__ mask,
-                     const int clip_h, const int clip_w, const NmsOut out) {
-  extern __shared__ __align__(16) unsigned long long sm[];   // [cap][stride] mask rows, [32] keep words
+nms_scan_smem_kernel(const CandSet set, const int wblocks, const int cap_pad,
+                     const unsigned long long* __restrict__ maskT, const int clip_h, const int clip_w,
+                     const NmsOut out) {
+  extern __shared__ __align__(16) unsigned long long sm[];   // packed columns
+  __shared__ unsigned long long keepw[32];
+  __shared__ unsigned nz[32];
   __shared__ int s_pre[33];
+  __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kSmemScanThreads / 32;
   const int b = blockIdx.x;
   B200DET_STAMP_NOSYNC(16);
   const int n = set.count[b];
-  const int W = (n + kNmsTile - 1) / kNmsTile;              // <= 20
-  const int stride = wcap | 1;
-  unsigned long long* M = sm;
-  unsigned long long* keepw = sm + (size_t)set.cap * stride;
+  const int W = (n + kNmsTile - 1) / kNmsTile;               // <= kSmemScanMaxBlocks
   const size_t o0 = (size_t)b * set.cap;
   const size_t q0 = (size_t)b * out.stride;
 
-  // stage rows [r0, r1): row i needs the words of its own block and the blocks ahead
-  // A warp covers 32 / wp2 rows per step (wp2 = W rounded up to a power of two <= 32), one 8-byte
-  // word per lane, so the copy loop is a handful of instructions per row.
-  int wp2 = 1;
-  while (wp2 < W) wp2 <<= 1;
-  const int sub = lane / wp2, wl = lane & (wp2 - 1), rows_per_step = 32 / wp2;
-  auto stage_rows = [&](int r0, int r1) {
-    for (int i = r0 + warp * rows_per_step + sub; i < r1; i += kWarps * rows_per_step)
-      if (wl >= (i >> 6) && wl < W) cp_async8(M + (size_t)i * stride + wl, mask + (o0 + i) * wcap + wl);
-    cp_async_commit();
-  };
-  const int split = min(n, 4 * kNmsTile);
-  stage_rows(0, split);
-  stage_rows(split, n);
-  if (tid < 32) keepw[tid] = 0ull;
-  cp_async_wait<1>();
-  __syncthreads();                                           // rows [0, split) resident
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+    if (W > 0) {
+      mbar_arrive_expect_tx(&bar, (uint32_t)(col_off(W) * 8));
+      for (int w = 0; w < W; ++w)
+        bulk_g2s(sm + col_off(w), maskT + ((size_t)b * wblocks + w) * cap_pad, (uint32_t)((w + 1) * kNmsTile * 8), &bar);
+    }
+  }
+  if (tid < 32) { keepw[tid] = 0ull; nz[tid] = 0u; }
+  __syncthreads();
+  if (W > 0) mbar_wait(&bar, 0);
   B200DET_STAMP_NOSYNC(17);
 
-  if (warp != 0) {
-    cp_async_wait<0>();
-    asm volatile("bar.arrive 1, %0;" ::"n"(kSmemScanThreads) : "memory");
-  } else {
-    unsigned long long myrem = 0ull;                         // lane w: removed-bitmap word w
-    bool rest_ready = false;
-    for (int rb = 0; rb < W; ++rb) {
-      if (rb == 4) {
-        cp_async_wait<0>();
-        asm volatile("bar.sync 1, %0;" ::"n"(kSmemScanThreads) : "memory");
-        rest_ready = true;
-      }
-      const int base = rb * kNmsTile;
-      const int rows = min(kNmsTile, n - base);
-      const unsigned long long valid = rows == kNmsTile ? ~0ull : ((1ull << rows) - 1ull);
-      const unsigned long long cur = shfl64(myrem, rb);
-      const size_t r0 = (size_t)(base + lane) * stride, r1 = (size_t)(base + lane + 32) * stride;
-      const unsigned long long d0 = (lane < rows) ? M[r0 + rb] : 0ull;
-      const unsigned long long d1 = (lane + 32 < rows) ? M[r1 + rb] : 0ull;
-      const bool a0 = !((cur >> lane) & 1ull), a1 = !((cur >> (lane + 32)) & 1ull);
-      const unsigned long long S = warp_or64((a0 ? d0 : 0ull) | (a1 ? d1 : 0ull));
-      unsigned long long keep;
-      if (((S & ~cur) & valid) == 0ull) {
-        keep = ~cur & valid;                                 // no alive row touches another alive row
-      } else {
-        unsigned long long c = cur;
-        keep = 0ull;
-#pragma unroll 8
-        for (int i = 0; i < kNmsTile; ++i) {
-          const unsigned long long di = shfl64(i < 32 ? d0 : d1, i & 31);
-          const bool alive = ((valid >> i) & 1ull) && !((c >> i) & 1ull);
-          keep |= alive ? (1ull << i) : 0ull;
-          c |= alive ? di : 0ull;
-        }
-      }
-      if (lane == 0) keepw[rb] = keep;
-      const bool k0 = (keep >> lane) & 1ull, k1 = (keep >> (lane + 32)) & 1ull;
-      for (int w = rb + 1; w < W; ++w) {
-        const unsigned long long v = warp_or64((k0 ? M[r0 + w] : 0ull) | (k1 ? M[r1 + w] : 0ull));
-        if (lane == w) myrem |= v;
-      }
-    }
-    if (!rest_ready) {
-      cp_async_wait<0>();
-      asm volatile("bar.sync 1, %0;" ::"n"(kSmemScanThreads) : "memory");
-    }
+  // non-zero flags: bit w of nz[rb] <=> some row of block rb has a bit in column block w (w >= rb)
+  for (int pair = warp; pair < W * W; pair += kWarps) {
+    const int rb = pair / W, w = pair - rb * W;
+    if (w < rb) continue;
+    const unsigned long long* col = sm + col_off(w) + rb * kNmsTile;
+    const bool any = __any_sync(0xffffffffu, (col[lane] | col[lane + 32]) != 0ull);
+    if (any && lane == 0) atomicOr(&nz[rb], 1u << w);
   }
   __syncthreads();
 
-  B200DET_STAMP_NOSYNC(18);
-  if (warp == 0) {                                           // exclusive prefix of kept counts per block
+  if (warp == 0) {
+    unsigned long long myrem = 0ull;                         // lane w: removed-bitmap word w
+    for (int rb = 0; rb < W; ++rb) {
+      const int rows = min(kNmsTile, n - rb * kNmsTile);
+      const unsigned long long valid = rows == kNmsTile ? ~0ull : ((1ull << rows) - 1ull);
+      const unsigned long long cur = shfl64(myrem, rb);
+      const unsigned flags = nz[rb];
+      unsigned long long keep;
+      if (!((flags >> rb) & 1u)) {
+        keep = ~cur & valid;                                 // empty diagonal tile
+      } else {
+        const unsigned long long* diag = sm + col_off(rb) + rb * kNmsTile;
+        keep = resolve_block(cur, valid, diag[lane], diag[lane + 32], lane);
+      }
+      if (lane == 0) keepw[rb] = keep;
+      const bool k0 = (keep >> lane) & 1ull, k1 = (keep >> (lane + 32)) & 1ull;
+      for (unsigned m = flags & ~((2u << rb) - 1u); m; m &= m - 1u) {     // flagged column blocks ahead
+        const int w = __ffs((int)m) - 1;
+        const unsigned long long* col = sm + col_off(w) + rb * kNmsTile;
+        const unsigned long long v = warp_or64((k0 ? col[lane] : 0ull) | (k1 ? col[lane + 32] : 0ull));
+        if (lane == w) myrem |= v;
+      }
+    }
+    // exclusive prefix of kept counts per block
+    __syncwarp();
     const int cnt = (lane < W) ? __popcll(keepw[lane]) : 0;
     int incl = cnt;
 #pragma unroll
@@ -376,6 +303,8 @@ nms_scan_smem_kernel(const CandSet set, const int wcap, const unsigned long long
     if (lane == 31) s_pre[32] = incl;
   }
   __syncthreads();
+  B200DET_STAMP_NOSYNC(18);
+
   // kept boxes in keep order; the gathers of all of a thread's rows are issued before any store
   constexpr int kRowsPerThread = (kSmemScanMaxCap + kSmemScanThreads - 1) / kSmemScanThreads;
   int oidx[kRowsPerThread];
@@ -398,23 +327,86 @@ nms_scan_smem_kernel(const CandSet set, const int wcap, const unsigned long long
     }
   }
 #pragma unroll
-  for (int u = 0; u < kRowsPerThread; ++u) {
-    if (oidx[u] < 0) continue;
-    float4 v = bx[u];
-    if (clip_h > 0) {   // ClipBoxes: clamp_(min=0), then x <= w-1, y <= h-1   (head.py:156-162)
-      v.x = clip1(v.x, (float)(clip_w - 1));
-      v.y = clip1(v.y, (float)(clip_h - 1));
-      v.z = clip1(v.z, (float)(clip_w - 1));
-      v.w = clip1(v.w, (float)(clip_h - 1));
-    }
-    const size_t o = q0 + oidx[u];
-    out.score[o] = sc[u];
-    out.cls[o] = (long long)cl[u];
-    out.keep[o] = (long long)sr[u];
-    reinterpret_cast<float4*>(out.box)[o] = v;
-  }
+  for (int u = 0; u < kRowsPerThread; ++u)
+    if (oidx[u] >= 0)
+      store_kept(set, out, o0, q0, tid + u * kSmemScanThreads, oidx[u], clip_h, clip_w, bx[u], sc[u], cl[u], sr[u]);
   B200DET_STAMP(19);
   if (tid == 0) out.count[b] = s_pre[32];
+}
+
+// ---- large-n variant: a ring of row-block chunks ------------------------------------------------
+// Chunk rb = the 64 rows of block rb for column blocks [rb, W): (W - rb) pieces of 512 bytes, one
+// bulk copy each, landing on the slot's mbarrier.  Warp 0 resolves the diagonal, all warps OR the
+// kept rows into the removed-bitmap (one column block per warp at a time), 64 threads write the
+// kept rows, then thread 0 refills the slot with the chunk kRingSlots blocks ahead.
+constexpr int kRingThreads = 256;
+constexpr int kRingSlots = 3;
+
+__global__ void __launch_bounds__(kRingThreads, 1)
+nms_scan_ring_kernel(const CandSet set, const int wblocks, const int cap_pad,
+                     const unsigned long long* __restrict__ maskT, const int clip_h, const int clip_w,
+                     const NmsOut out) {
+  extern __shared__ __align__(16) unsigned long long sm[];   // [kRingSlots][wblocks*64] chunks, [wblocks] removed
+  __shared__ unsigned long long s_keep;
+  __shared__ __align__(8) uint64_t bars[kRingSlots];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = kRingThreads / 32;
+  const int b = blockIdx.x;
+  const int n = set.count[b];
+  const int W = (n + kNmsTile - 1) / kNmsTile;
+  const int slot_words = wblocks * kNmsTile;
+  unsigned long long* removed = sm + (size_t)kRingSlots * slot_words;
+  const size_t o0 = (size_t)b * set.cap;
+  const size_t q0 = (size_t)b * out.stride;
+
+  auto issue = [&](int rb) {                                 // thread 0 only
+    const int slot = rb % kRingSlots;
+    mbar_arrive_expect_tx(&bars[slot], (uint32_t)((W - rb) * kNmsTile * 8));
+    for (int w = rb; w < W; ++w)
+      bulk_g2s(sm + (size_t)slot * slot_words + (w - rb) * kNmsTile,
+               maskT + ((size_t)b * wblocks + w) * cap_pad + rb * kNmsTile, kNmsTile * 8, &bars[slot]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kRingSlots; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+    for (int rb = 0; rb < min(kRingSlots, W); ++rb) issue(rb);
+  }
+  for (int w = tid; w < wblocks; w += kRingThreads) removed[w] = 0ull;
+  __syncthreads();
+
+  int total = 0;
+  for (int rb = 0; rb < W; ++rb) {
+    const int slot = rb % kRingSlots;
+    mbar_wait(&bars[slot], (uint32_t)((rb / kRingSlots) & 1));
+    const unsigned long long* chunk = sm + (size_t)slot * slot_words;
+    const int rows = min(kNmsTile, n - rb * kNmsTile);
+    const unsigned long long valid = rows == kNmsTile ? ~0ull : ((1ull << rows) - 1ull);
+    if (warp == 0) {
+      const unsigned long long keep = resolve_block(removed[rb], valid, chunk[lane], chunk[lane + 32], lane);
+      if (lane == 0) s_keep = keep;
+    }
+    __syncthreads();
+    const unsigned long long keep = s_keep;
+    const bool k0 = (keep >> lane) & 1ull, k1 = (keep >> (lane + 32)) & 1ull;
+    for (int w = rb + 1 + warp; w < W; w += kWarps) {        // one column block per warp: no atomics
+      const unsigned long long* col = chunk + (w - rb) * kNmsTile;
+      const unsigned long long v = warp_or64((k0 ? col[lane] : 0ull) | (k1 ? col[lane + 32] : 0ull));
+      if (lane == 0 && v) removed[w] |= v;
+    }
+    if (tid < kNmsTile && ((keep >> tid) & 1ull)) {
+      const int q = rb * kNmsTile + tid;
+      const int o = total + __popcll(keep & ((1ull << tid) - 1ull));
+      store_kept(set, out, o0, q0, q, o, clip_h, clip_w, reinterpret_cast<const float4*>(set.box)[o0 + q],
+                 set.score[o0 + q], set.cls[o0 + q], set.src[o0 + q]);
+    }
+    total += __popcll(keep);
+    __syncthreads();                                         // removed[] complete; slot free
+    if (tid == 0 && rb + kRingSlots < W) {
+      fence_proxy_async_smem();                              // generic reads of the slot before the async refill
+      issue(rb + kRingSlots);
+    }
+  }
+  if (tid == 0) out.count[b] = total;
 }
 
 struct NmsWorkspace {
@@ -422,6 +414,8 @@ struct NmsWorkspace {
   unsigned long long* mask;
   size_t bytes;
 };
+
+inline int nms_blocks(int cap) { return (cap + kNmsTile - 1) / kNmsTile; }
 
 // carve the candidate set + mask out of a workspace (base may be null to size only)
 NmsWorkspace carve_nms(void* base, int batch, int cap) {
@@ -441,9 +435,19 @@ NmsWorkspace carve_nms(void* base, int batch, int cap) {
   w.set.count = reinterpret_cast<int32_t*>(take((size_t)batch * 4));
   w.set.mode = reinterpret_cast<int32_t*>(take((size_t)batch * 4));
   w.set.cap = cap;
-  w.mask = reinterpret_cast<unsigned long long*>(take(bc * nms_mask_words(cap) * 8));
+  // maskT[batch][blocks][blocks * 64] words
+  w.mask = reinterpret_cast<unsigned long long*>(take((size_t)batch * nms_blocks(cap) * nms_blocks(cap) * kNmsTile * 8));
   w.bytes = off;
   return w;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t smem) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
+  }
+  return B200DET_OK;
 }
 
 }  // namespace
@@ -458,34 +462,27 @@ void nms_set_carve(void* base, int batch, int cap, CandSet* set, unsigned long l
 
 int launch_nms(const CandSet& set, int batch, double nms_thr, int clip_h, int clip_w,
                unsigned long long* mask, const NmsOut& out, cudaStream_t stream) {
-  const int wcap = nms_mask_words(set.cap);
   // smallest fp32 F with (double)F > thr: for a non-NaN fp32 iou, (double)iou > thr  <=>  iou >= F
   float thr_up = (float)nms_thr;
   if (!((double)thr_up > nms_thr)) thr_up = nextafterf(thr_up, INFINITY);
   const bool zero_suppresses = !(nms_thr >= 0.0);
-  const int wblocks = (set.cap + kNmsTile - 1) / kNmsTile;
+  const int wblocks = nms_blocks(set.cap);
+  const int cap_pad = wblocks * kNmsTile;
   if (zero_suppresses)
-    nms_mask_kernel<true><<<dim3(wblocks, wblocks, batch), kNmsTile, 0, stream>>>(set, wcap, thr_up, mask);
+    nms_mask_kernel<true><<<dim3(wblocks, wblocks, batch), kNmsTile, 0, stream>>>(set, wblocks, cap_pad, thr_up, mask);
   else
-    nms_mask_kernel<false><<<dim3(wblocks, wblocks, batch), kNmsTile, 0, stream>>>(set, wcap, thr_up, mask);
+    nms_mask_kernel<false><<<dim3(wblocks, wblocks, batch), kNmsTile, 0, stream>>>(set, wblocks, cap_pad, thr_up, mask);
   int rc = check_launch();
   if (rc) return rc;
-  if (set.cap <= kSmemScanMaxCap) {
-    const size_t smem = ((size_t)set.cap * (wcap | 1) + 32) * sizeof(unsigned long long);
-    if (smem > 48 * 1024) {
-      cudaError_t e =
-          cudaFuncSetAttribute(nms_scan_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
-    }
-    nms_scan_smem_kernel<<<batch, kSmemScanThreads, smem, stream>>>(set, wcap, mask, clip_h, clip_w, out);
+  if (wblocks <= kSmemScanMaxBlocks) {
+    const size_t smem = (size_t)kNmsTile * (wblocks * (wblocks + 1) / 2) * sizeof(unsigned long long);
+    if ((rc = set_smem(nms_scan_smem_kernel, smem))) return rc;
+    nms_scan_smem_kernel<<<batch, kSmemScanThreads, smem, stream>>>(set, wblocks, cap_pad, mask, clip_h, clip_w, out);
     return check_launch();
   }
-  const size_t smem = ((size_t)2 * kNmsTile * wcap + wcap) * sizeof(unsigned long long);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
-  }
-  nms_scan_kernel<<<batch, kScanThreads, smem, stream>>>(set, wcap, mask, clip_h, clip_w, out);
+  const size_t smem = ((size_t)kRingSlots * wblocks * kNmsTile + wblocks) * sizeof(unsigned long long);
+  if ((rc = set_smem(nms_scan_ring_kernel, smem))) return rc;
+  nms_scan_ring_kernel<<<batch, kRingThreads, smem, stream>>>(set, wblocks, cap_pad, mask, clip_h, clip_w, out);
   return check_launch();
 }
 
@@ -515,13 +512,11 @@ extern "C" int b200det_batched_nms(int batch, int n, const float* boxes, const f
   int n2 = 1;
   while (n2 < n) n2 <<= 1;
   const size_t smem = (size_t)n2 * 8 + (size_t)n * 4;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(nms_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
-  }
+  int rc = set_smem(nms_prepare_kernel, smem);
+  if (rc) return rc;
   nms_prepare_kernel<<<batch, kPrepThreads, smem, st>>>(n, boxes, scores, reinterpret_cast<const long long*>(classes),
                                                        in_count, score_thr, set);
-  int rc = check_launch();
+  rc = check_launch();
   if (rc) return rc;
   NmsOut out{out_score, reinterpret_cast<long long*>(out_cls), out_box, reinterpret_cast<long long*>(out_keep),
              out_count, n};
