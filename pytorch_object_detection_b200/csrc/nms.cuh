@@ -52,9 +52,6 @@ struct NmsOut {
   int stride;
 };
 
-// words per mask row for a capacity of `cap` boxes (even, so rows are 16-byte aligned)
-inline int nms_mask_words(int cap) { return ((cap + 63) / 64 + 1) & ~1; }
-
 // candidate set + suppression mask carved out of one caller-owned workspace
 size_t nms_set_workspace_bytes(int batch, int cap);
 void nms_set_carve(void* base, int batch, int cap, CandSet* set, unsigned long long** mask);

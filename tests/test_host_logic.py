@@ -1,0 +1,176 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol of include/b200det.h, argument
+validation happens before any CUDA call, the drop-in modules keep the reference's error behaviour,
+and the multi-rank sharding / gather logic is exact (gloo, world_size 2).  No GPU needed."""
+import ctypes as C
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import pytorch_object_detection_b200 as P
+from oracle import fcos_oracle as O
+from pytorch_object_detection_b200 import _lib, sharding, workloads as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "b200det.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200det_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/b200det.h but not exported"
+    assert sorted(_lib.PROTOTYPES) == names, "ctypes prototypes and header disagree"
+    assert lib.b200det_abi_version() == _lib.ABI_VERSION
+    assert lib.b200det_status_string(0) == b"ok"
+    assert b"workspace" in lib.b200det_status_string(3)
+
+
+def test_header_is_plain_c():
+    import subprocess
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                          os.path.join(ROOT, "include", "b200det.h")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
+def test_workspace_sizes_are_host_only_and_monotone():
+    lib = _lib.load()
+    a = lib.b200det_postprocess_workspace_bytes(16, 23265, 1000)
+    b = lib.b200det_postprocess_workspace_bytes(32, 23265, 1000)
+    c = lib.b200det_postprocess_workspace_bytes(16, 23265, 5000)
+    assert 0 < a < b and a < c
+    assert a >= 16 * 23265 * 6 + 16 * 16 * 16 * 64 * 8          # scores + classes + mask tiles
+    assert lib.b200det_postprocess_workspace_bytes(16, 23265, _lib.MAX_BOX + 1) == 0
+    assert lib.b200det_nms_workspace_bytes(1, 0) == 0
+    assert lib.b200det_nms_workspace_bytes(4, 1000) > 4 * 1000 * 44
+    assert lib.b200det_cls_loss_workspace_bytes(32, 23265) >= 32 * 46 * 4
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
+    lib = _lib.load()
+    lv = _lib.make_levels([(0, 0, 0, 4, 4, 8)])
+    # null outputs / workspace
+    assert lib.b200det_postprocess(lv, 1, 1, 20, 0.05, 0.6, 100, 0, 0, None, 0, None, None, None, None, None, None) == 1
+    assert lib.b200det_score_points(lv, 1, 1, 20, None, None, None) == 1
+    assert lib.b200det_score_points(lv, 0, 1, 20, None, None, None) == 1
+    assert lib.b200det_batched_nms(1, 10, None, None, None, None, 0.0, 0.5, 0, 0, None, 0, None, None, None, None,
+                                   None, None) == 1
+    assert lib.b200det_assign_targets(None, None, None, None, None, 1, 1, 1, None, None, None, None, None, None,
+                                      None) == 1
+    assert lib.b200det_clip_boxes(None, 5, 10, 10, None) == 1
+    assert lib.b200det_clip_boxes(None, 0, 10, 10, None) == 0           # nothing to do is fine
+    with pytest.raises(_lib.B200DetError):
+        _lib.make_levels([(0, 0, 0, 1, 1, 1)] * 9)                      # more than B200DET_MAX_LEVELS
+    with pytest.raises(_lib.B200DetError, match="bad argument"):
+        _lib.check(1, "x")
+
+
+def test_modules_have_no_cpu_path_and_keep_reference_errors():
+    x = W.head_outputs(1, 20, W.VOC_LEVELS, seed=3)
+    head = P.FCOSHead(0.05, 0.6, 1000, W.STRIDES)
+    assert (head.score, head.nms_threshold, head.max_box, head.strides) == (0.05, 0.6, 1000, W.STRIDES)
+    with pytest.raises(Exception):
+        head(x)                                                          # CPU tensors: refused, not emulated
+    with pytest.raises(Exception):
+        P.ClipBoxes()(torch.zeros(1, 3, 8, 8), torch.zeros(1, 2, 4))
+    gen = P.FCOSGenTargets(W.STRIDES, W.FCOS_RANGES)
+    with pytest.raises(AssertionError):
+        P.FCOSGenTargets(W.STRIDES, W.FCOS_RANGES[:4])                   # head.py:216
+    with pytest.raises(AssertionError):
+        gen([[x[0][:4], x[1][:4], x[2][:4]], torch.zeros(1, 2, 4), torch.zeros(1, 2, dtype=torch.long)])  # head.py:225
+    with pytest.raises(Exception):
+        gen([x, torch.zeros(1, 2, 4), torch.zeros(1, 2, dtype=torch.long)])
+    with pytest.raises(NotImplementedError):                             # loss.py:137-138
+        P.compute_reg_loss(x[2], torch.zeros(1, W.num_points(W.VOC_LEVELS), 4),
+                           torch.zeros(1, W.num_points(W.VOC_LEVELS), dtype=torch.bool), mode="diou")
+    with pytest.raises(AssertionError):                                  # loss.py:127 shape check
+        P.compute_reg_loss(x[2], torch.zeros(1, 7, 4), torch.zeros(1, 7, dtype=torch.bool), mode="iou")
+    assert P.FCOSLoss().mode == "giou" and P.FCOSLoss("iou").mode == "iou"
+
+
+def test_shard_bounds_partition_the_batch():
+    for batch in (1, 2, 7, 16, 255, 256):
+        for world in (1, 2, 3, 4, 8):
+            spans = [sharding.shard_bounds(batch, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == batch
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(4, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, batch, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    x = W.head_outputs(batch, 5, W.VOC_LEVELS[2:], seed=9)            # small: 16x16 .. 4x4 levels
+    strides = W.STRIDES[2:]
+    mine = sharding.shard_levels(x, world, rank)
+    k = 50
+    dets = O.detect(mine, 0.05, 0.6, k, strides)                       # the CPU oracle stands in for the kernels
+    nb = len(dets)
+    scores = torch.zeros(nb, k)
+    classes = torch.zeros(nb, k, dtype=torch.int64)
+    boxes = torch.zeros(nb, k, 4)
+    counts = torch.zeros(nb, dtype=torch.int32)
+    for i, (s, c, b) in enumerate(dets):
+        n = s.numel()
+        scores[i, :n], classes[i, :n], boxes[i, :n], counts[i] = s, c, b, n
+    full = sharding.gather_detections(scores, classes, boxes, counts, batch)
+    per_image = [torch.arange(nb, dtype=torch.float32) + 10 * rank + 1]
+    red = sharding.reduce_image_losses(per_image, batch)
+    if rank == 0:
+        torch.save({"full": full, "red": red}, os.path.join(out_dir, "out.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch", [5, 6])
+def test_two_rank_gather_matches_single_process(tmp_path, batch):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), batch, str(tmp_path)), nprocs=world, join=True)
+    got = torch.load(os.path.join(str(tmp_path), "out.pt"))
+    x = W.head_outputs(batch, 5, W.VOC_LEVELS[2:], seed=9)
+    want = O.detect(x, 0.05, 0.6, 50, W.STRIDES[2:])
+    scores, classes, boxes, counts = got["full"]
+    assert scores.shape[0] == batch and counts.shape[0] == batch
+    for i, (s, c, b) in enumerate(want):
+        n = int(counts[i])
+        assert n == s.numel()
+        assert torch.equal(scores[i, :n], s) and torch.equal(classes[i, :n], c) and torch.equal(boxes[i, :n], b)
+    # per-image "losses": rank r holds arange(nb) + 10 r + 1
+    sizes = [sharding.shard_bounds(batch, world, r) for r in range(world)]
+    total = sum(float((torch.arange(hi - lo, dtype=torch.float32) + 10 * r + 1).sum()) for r, (lo, hi) in enumerate(sizes))
+    assert float(got["red"][0]) == pytest.approx(total / batch, rel=1e-6)
+
+
+def test_sharded_oracle_equals_full_batch():
+    """Images are independent: running shards separately gives the same per-image result."""
+    x = W.head_outputs(3, 20, W.VOC_LEVELS, seed=21)
+    full = O.detect(x, 0.05, 0.6, 1000, W.STRIDES)
+    for world in (2, 3):
+        got = []
+        for r in range(world):
+            got += O.detect(sharding.shard_levels(x, world, r), 0.05, 0.6, 1000, W.STRIDES)
+        for a, b in zip(got, full):
+            assert all(torch.equal(p, q) for p, q in zip(a, b))
