@@ -176,12 +176,20 @@ def main():
     head = B.FCOSHead(SCORE_THR, NMS_THR, MAX_BOX, W.STRIDES)
     sampler = ClockSampler(local)
 
+    from pytorch_object_detection_b200 import sharding
+    gathered = {}
+
     def gather(outs):
+        """The path's only collective: ONE all_gather of the shard's packed detections (scores, boxes,
+        classes, keep indices and counts share one allocation) into a preallocated [world, bytes] buffer."""
         if dist is None:
             return
-        for t in outs:
-            full = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-            dist.all_gather_into_tensor(full, t.contiguous())
+        key = outs[0].data_ptr()
+        if key not in gathered:
+            packed = sharding.packed_of(outs[0])
+            gathered[key] = (packed, packed.new_empty((world, packed.numel())))
+        packed, full = gathered[key]
+        dist.all_gather_into_tensor(full, packed)
 
     # One CUDA graph per input set: FCOSHead.detect (4 kernel launches) captured once, replayed per
     # step, so the timed loop is not bound by Python/ctypes launch overhead.  The NCCL gather of the

@@ -103,11 +103,7 @@ def postprocess(cls: Sequence[Tensor], cnt: Sequence[Tensor], reg: Sequence[Tens
     ncls = keep_alive[0].shape[1]
     ws_bytes = lib.b200det_postprocess_workspace_bytes(batch, p_total, k)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    scores = torch.empty((batch, k), dtype=torch.float32, device=dev)
-    classes = torch.empty((batch, k), dtype=torch.int64, device=dev)
-    boxes = torch.empty((batch, k, 4), dtype=torch.float32, device=dev)
-    keep = torch.empty((batch, k), dtype=torch.int64, device=dev)
-    counts = torch.empty((batch,), dtype=torch.int32, device=dev)
+    scores, classes, boxes, keep, counts = detection_views(packed_detections(batch, k, dev), batch, k)
     ch, cw = (int(clip_hw[0]), int(clip_hw[1])) if clip_hw else (0, 0)
     with torch.cuda.device(dev):
         rc = lib.b200det_postprocess(lv, n, batch, ncls, float(score_thr), float(nms_thr), k, ch, cw,
@@ -115,6 +111,36 @@ def postprocess(cls: Sequence[Tensor], cnt: Sequence[Tensor], reg: Sequence[Tens
                                      boxes.data_ptr(), keep.data_ptr(), counts.data_ptr(), _stream(ws))
     _lib.check(rc, "b200det_postprocess")
     _count("postprocess")
+    return scores, classes, boxes, keep, counts
+
+
+def _packed_layout(batch: int, k: int):
+    """Byte offsets of (scores f32, boxes f32x4, classes i64, keep i64, counts i32) in one buffer."""
+    sizes = [batch * k * 4, batch * k * 16, batch * k * 8, batch * k * 8, batch * 4]
+    offs, off = [], 0
+    for sz in sizes:
+        offs.append(off)
+        off += (sz + 255) // 256 * 256
+    return offs, sizes, off
+
+
+def packed_detections(batch: int, k: int, device) -> Tensor:
+    """One contiguous uint8 buffer holding every post-process output of a [batch, k] shard, so that a
+    multi-rank gather is a single collective (see sharding.gather_packed)."""
+    return torch.empty(_packed_layout(batch, k)[2], dtype=torch.uint8, device=device)
+
+
+def detection_views(packed: Tensor, batch: int, k: int):
+    """Typed views (scores, classes, boxes, keep, counts) into a packed_detections buffer (or into one
+    rank's slice of a gathered buffer)."""
+    offs, sizes, total = _packed_layout(batch, k)
+    assert packed.numel() == total and packed.dtype == torch.uint8
+    part = [packed[o:o + n] for o, n in zip(offs, sizes)]
+    scores = part[0].view(torch.float32).view(batch, k)
+    boxes = part[1].view(torch.float32).view(batch, k, 4)
+    classes = part[2].view(torch.int64).view(batch, k)
+    keep = part[3].view(torch.int64).view(batch, k)
+    counts = part[4].view(torch.int32).view(batch)
     return scores, classes, boxes, keep, counts
 
 

@@ -64,6 +64,27 @@ def gather_detections(scores: Tensor, classes: Tensor, boxes: Tensor, counts: Te
     return tuple(gathered)
 
 
+def gather_packed(packed: Tensor, out: Tensor | None = None, group=None) -> Tensor:
+    """ONE collective for a whole shard: all-gather the packed detection buffer of
+    ``ops.postprocess`` (scores, boxes, classes, keep, counts share one allocation: the scores
+    tensor's storage).  Every rank must hold the same shard size.  Returns ``[world, bytes]`` uint8;
+    ``ops.detection_views(out[r], batch_per_rank, k)`` gives rank r's typed tensors."""
+    world = dist.get_world_size(group)
+    if out is None:
+        out = packed.new_empty((world, packed.numel()))
+    if packed.is_cuda:
+        dist.all_gather_into_tensor(out, packed, group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), packed, group=group)
+    return out
+
+
+def packed_of(scores: Tensor) -> Tensor:
+    """The packed uint8 buffer behind the outputs of ``ops.postprocess`` / ``FCOSHead.detect``."""
+    st = scores.untyped_storage()
+    return torch.empty(0, dtype=torch.uint8, device=scores.device).set_(st, 0, (st.nbytes(),))
+
+
 def reduce_image_losses(per_image: Sequence[Tensor], batch: int, group=None) -> List[Tensor]:
     """Batch means of per-image losses computed on shards: sum(shard) / batch, all-reduced.
 

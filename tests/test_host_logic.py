@@ -140,8 +140,17 @@ def _worker(rank, world, port, batch, out_dir):
     full = sharding.gather_detections(scores, classes, boxes, counts, batch)
     per_image = [torch.arange(nb, dtype=torch.float32) + 10 * rank + 1]
     red = sharding.reduce_image_losses(per_image, batch)
+    packed_all = None
+    if batch % world == 0:                                            # single-collective packed gather
+        from pytorch_object_detection_b200 import ops
+        pk = ops.packed_detections(nb, k, "cpu")
+        pk.zero_()
+        for dst, src in zip(ops.detection_views(pk, nb, k), (scores, classes, boxes, classes, counts)):
+            dst.copy_(src)
+        assert sharding.packed_of(ops.detection_views(pk, nb, k)[0]).data_ptr() == pk.data_ptr()
+        packed_all = sharding.gather_packed(pk)
     if rank == 0:
-        torch.save({"full": full, "red": red}, os.path.join(out_dir, "out.pt"))
+        torch.save({"full": full, "red": red, "packed": packed_all}, os.path.join(out_dir, "out.pt"))
     dist.destroy_process_group()
 
 
@@ -158,6 +167,16 @@ def test_two_rank_gather_matches_single_process(tmp_path, batch):
         n = int(counts[i])
         assert n == s.numel()
         assert torch.equal(scores[i, :n], s) and torch.equal(classes[i, :n], c) and torch.equal(boxes[i, :n], b)
+    if got["packed"] is not None:
+        from pytorch_object_detection_b200 import ops
+        nb = batch // world
+        for r in range(world):
+            ps, pc, pb, _, pn = ops.detection_views(got["packed"][r], nb, 50)
+            for i in range(nb):
+                n = int(pn[i])
+                s, c, b = want[r * nb + i]
+                assert n == s.numel() and torch.equal(ps[i, :n], s) and torch.equal(pc[i, :n], c)
+                assert torch.equal(pb[i, :n], b)
     # per-image "losses": rank r holds arange(nb) + 10 r + 1
     sizes = [sharding.shard_bounds(batch, world, r) for r in range(world)]
     total = sum(float((torch.arange(hi - lo, dtype=torch.float32) + 10 * r + 1).sum()) for r, (lo, hi) in enumerate(sizes))
