@@ -105,7 +105,12 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
   do {                                                                               \
     if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_trace[slot] = clock64(); \
   } while (0)
+#define B200DET_STAMP_IF(cond, slot)                                                 \
+  do {                                                                               \
+    if ((cond) && threadIdx.x == 0) g_trace[slot] = clock64();                       \
+  } while (0)
 #else
+#define B200DET_STAMP_IF(cond, slot) do {} while (0)
 #define B200DET_TRACE_BUFFER(name)
 #define B200DET_STAMP(slot) do {} while (0)
 #define B200DET_STAMP_NOSYNC(slot) do {} while (0)
