@@ -1,6 +1,7 @@
 // C-ABI glue: status strings, the fused post-process entry (K1 -> K2 -> K3) and ClipBoxes.
 #include "nms.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace b200det {
@@ -114,10 +115,15 @@ extern "C" int b200det_postprocess(const b200det_level* levels, int n_levels, in
 
   int rc = launch_score_points(lt, batch, num_classes, w.score, w.cls0, st);
   if (rc) return rc;
-  rc = launch_select_topk(lt, batch, w.score, w.cls0, score_thr, max_box, set, nullptr, st);
-  if (rc) return rc;
   NmsOut out{out_score, reinterpret_cast<long long*>(out_cls), out_box, reinterpret_cast<long long*>(out_keep),
              out_count, max_box};
+  // K2 + K3: one fused kernel (one CTA per image) when the candidate set fits (<= 1024), else three kernels.
+  // B200DET_NO_FUSED=1 forces the three-kernel chain (A/B testing; results are bit-identical).
+  static const bool no_fused = getenv("B200DET_NO_FUSED") && getenv("B200DET_NO_FUSED")[0] == '1';
+  if (!no_fused && fused_supported(lt, max_box, nms_thr))
+    return launch_fused_select_nms(lt, batch, w.score, w.cls0, score_thr, max_box, set, nms_thr, clip_h, clip_w, out, st);
+  rc = launch_select_topk(lt, batch, w.score, w.cls0, score_thr, max_box, set, nullptr, st);
+  if (rc) return rc;
   return launch_nms(set, batch, nms_thr, clip_h, clip_w, mask, out, st);
 }
 

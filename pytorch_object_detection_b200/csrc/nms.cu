@@ -16,7 +16,7 @@
 //       registers / shared memory; kept boxes are written (clipped when asked) in keep order.
 // This stage is latency-bound (the greedy dependency chain), not bandwidth-bound.
 #include "block_utils.cuh"
-#include "nms.cuh"
+#include "nms_body.cuh"
 #include "tma.cuh"
 
 B200DET_TRACE_BUFFER(nms)
@@ -130,31 +130,7 @@ nms_mask_kernel(const CandSet set, const int wblocks, const int cap_pad, const f
                           : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
   const float aarea = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
   const int acls = row_ok ? set.cls[o0 + i] : -2;
-  // pass 1: candidate bit j <=> the boxes overlap with positive area
-  const unsigned cbase = (unsigned)__cvta_generic_to_shared(cbox);
-  unsigned lo = 0u, hi = 0u;
-#pragma unroll
-  for (int j = 0; j < kNmsTile; ++j) {
-    float4 c;                                       // same address in every lane: broadcast LDS.128
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "r"(cbase + j * 16));
-    const bool overlap = ZERO_SUP || (fminf(a.z, c.z) > fmaxf(a.x, c.x) && fminf(a.w, c.w) > fmaxf(a.y, c.y));
-    if (j < 32) lo |= overlap ? (1u << j) : 0u;
-    else hi |= overlap ? (1u << (j - 32)) : 0u;
-  }
-  unsigned long long bits = ((unsigned long long)hi << 32) | lo;
-  // pass 2 (rare): the reference's exact IoU expression for the candidates only
-  for (unsigned long long m = bits; m; m &= m - 1ull) {
-    const int j = __ffsll((long long)m) - 1;
-    const float4 c = cbox[j];
-    const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, c.z), fmaxf(a.x, c.x)));
-    const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, c.w), fmaxf(a.y, c.y)));
-    const float inter = __fmul_rn(w, h);
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, carea[j]), inter));
-    bool sup = ovr >= thr_up;                        // == (double)ovr > thr, see launch_nms
-    if (same_class_only) sup = sup && (ccls[j] == acls);
-    if (!sup) bits &= ~(1ull << j);
-  }
+  unsigned long long bits = mask_row_bits<ZERO_SUP>(a, aarea, acls, cbox, carea, ccls, thr_up, same_class_only);
   if (cb == rb) bits &= ~((2ull << t) - 1ull);     // diagonal tile: only later boxes (j > t)
   if (!row_ok) bits = 0ull;
   maskT[((size_t)b * wblocks + cb) * cap_pad + i] = bits;   // 64 consecutive words per tile
@@ -163,57 +139,6 @@ nms_mask_kernel(const CandSet set, const int wblocks, const int cap_pad, const f
 // ------------------------------------------------------------------------------------------
 // greedy pass + output
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float clip1(float v, float hi) { return fminf(fmaxf(v, 0.f), hi); }
-
-__device__ __forceinline__ unsigned long long warp_or64(unsigned long long v) {
-  const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
-  const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
-  return ((unsigned long long)hi << 32) | lo;
-}
-__device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int src) {
-  const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);
-  const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
-  return ((unsigned long long)hi << 32) | lo;
-}
-
-// Resolve one 64-row block given the already-removed bits `cur` and the block's diagonal words
-// held lane-per-row (d0: row lane, d1: row lane+32).  If no still-alive row suppresses another
-// still-alive row (one warp OR-reduction) all alive rows are kept at once; otherwise the 64 rows
-// are walked serially out of registers (shuffles), the greedy rule of torchvision's nms kernel.
-__device__ __forceinline__ unsigned long long resolve_block(const unsigned long long cur, const unsigned long long valid,
-                                                            const unsigned long long d0, const unsigned long long d1,
-                                                            const int lane) {
-  const bool a0 = !((cur >> lane) & 1ull), a1 = !((cur >> (lane + 32)) & 1ull);
-  const unsigned long long S = warp_or64((a0 ? d0 : 0ull) | (a1 ? d1 : 0ull));
-  if (((S & ~cur) & valid) == 0ull) return ~cur & valid;
-  unsigned long long c = cur, keep = 0ull;
-#pragma unroll 8
-  for (int i = 0; i < kNmsTile; ++i) {
-    const unsigned long long di = shfl64(i < 32 ? d0 : d1, i & 31);
-    const bool alive = ((valid >> i) & 1ull) && !((c >> i) & 1ull);
-    keep |= alive ? (1ull << i) : 0ull;
-    c |= alive ? di : 0ull;
-  }
-  return keep;
-}
-
-// gather + (optional) clip + store of one kept row
-__device__ __forceinline__ void store_kept(const CandSet& set, const NmsOut& out, const size_t o0, const size_t q0,
-                                           const int q, const int o, const int clip_h, const int clip_w,
-                                           const float4 bx, const float sc, const int cl, const int sr) {
-  float4 v = bx;
-  if (clip_h > 0) {   // ClipBoxes: clamp_(min=0), then x <= w-1, y <= h-1   (head.py:156-162)
-    v.x = clip1(v.x, (float)(clip_w - 1));
-    v.y = clip1(v.y, (float)(clip_h - 1));
-    v.z = clip1(v.z, (float)(clip_w - 1));
-    v.w = clip1(v.w, (float)(clip_h - 1));
-  }
-  out.score[q0 + o] = sc;
-  out.cls[q0 + o] = (long long)cl;
-  out.keep[q0 + o] = (long long)sr;
-  reinterpret_cast<float4*>(out.box)[q0 + o] = v;
-}
-
 // ---- small-n variant: the image's whole upper-triangular mask resident in shared memory ------
 // cap <= kSmemScanMaxCap (every reference configuration: max_detection_box = 1000).  Column block w
 // holds the words of rows [0, (w+1)*64); thread 0 issues one bulk copy per column block, all of
@@ -223,7 +148,6 @@ constexpr int kSmemScanThreads = 256;
 constexpr int kSmemScanMaxBlocks = 28;                       // 28*29/2 * 512 B = 203 KB
 constexpr int kSmemScanMaxCap = kSmemScanMaxBlocks * kNmsTile;   // 1792
 
-__device__ __forceinline__ int col_off(int w) { return kNmsTile * (w * (w + 1) / 2); }   // words before column w
 
 __global__ void __launch_bounds__(kSmemScanThreads, 1)
 nms_scan_smem_kernel(const CandSet set, const int wblocks, const int cap_pad,
@@ -460,12 +384,18 @@ void nms_set_carve(void* base, int batch, int cap, CandSet* set, unsigned long l
   *mask = w.mask;
 }
 
+void nms_threshold_params(double nms_thr, float* thr_up, bool* zero_sup) {
+  float f = (float)nms_thr;
+  if (!((double)f > nms_thr)) f = nextafterf(f, INFINITY);
+  *thr_up = f;
+  *zero_sup = !(nms_thr >= 0.0);
+}
+
 int launch_nms(const CandSet& set, int batch, double nms_thr, int clip_h, int clip_w,
                unsigned long long* mask, const NmsOut& out, cudaStream_t stream) {
-  // smallest fp32 F with (double)F > thr: for a non-NaN fp32 iou, (double)iou > thr  <=>  iou >= F
-  float thr_up = (float)nms_thr;
-  if (!((double)thr_up > nms_thr)) thr_up = nextafterf(thr_up, INFINITY);
-  const bool zero_suppresses = !(nms_thr >= 0.0);
+  float thr_up;
+  bool zero_suppresses;
+  nms_threshold_params(nms_thr, &thr_up, &zero_suppresses);
   const int wblocks = nms_blocks(set.cap);
   const int cap_pad = wblocks * kNmsTile;
   if (zero_suppresses)

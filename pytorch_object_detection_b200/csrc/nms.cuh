@@ -52,6 +52,17 @@ struct NmsOut {
   int stride;
 };
 
+// (double)iou > thr for a non-NaN fp32 iou  <=>  iou >= thr_up, the smallest fp32 strictly above thr
+// (torchvision's CPU kernel compares the fp32 IoU with a double threshold).  zero_sup: thr < 0 (or
+// NaN), where even a zero IoU suppresses and the overlap shortcut must not be taken.
+void nms_threshold_params(double nms_thr, float* thr_up, bool* zero_sup);
+
+// K2 + K3 as one kernel (fused.cu), for max_box <= 1024 and nms_thr >= 0
+bool fused_supported(const LevelTable& lt, int max_box, double nms_thr);
+int launch_fused_select_nms(const LevelTable& lt, int batch, const float* score, const int16_t* cls0, float thr,
+                            int max_box, const CandSet& set, double nms_thr, int clip_h, int clip_w,
+                            const NmsOut& out, cudaStream_t stream);
+
 // candidate set + suppression mask carved out of one caller-owned workspace
 size_t nms_set_workspace_bytes(int batch, int cap);
 void nms_set_carve(void* base, int batch, int cap, CandSet* set, unsigned long long** mask);

@@ -21,7 +21,9 @@ for _ in range(3):
     head.detect(x, clip_hw=W.COCO_HW)
 torch.cuda.synchronize()
 t = [0] * 64
-for name, lo, hi in (("select", 0, 8), ("nms", 16, 20)):
+import os as _os
+fused = _os.environ.get("B200DET_NO_FUSED") != "1"
+for name, lo, hi in ((("fused", 0, 12),) if fused else (("select", 0, 8), ("nms", 16, 20))):
     buf = (C.c_longlong * 64)()
     fn = getattr(lib, "b200det_debug_read_trace_" + name)
     fn.argtypes = [C.c_void_p, C.c_int]
@@ -29,8 +31,9 @@ for name, lo, hi in (("select", 0, 8), ("nms", 16, 20)):
     t[lo:hi] = list(buf)[lo:hi]
 names = {0: "K2 start", 1: "K2 keys loaded + min/max", 2: "K2 phase A (block passes)", 3: "K2 phase B (warp finish)",
          4: "K2 tie + compaction", 5: "K2 sort", 6: "K2 gather/decode", 7: "K2 nms boxes",
+         8: "F select done", 9: "F class-bucket sparse mask", 10: "F greedy pass", 11: "F outputs",
          16: "K3 scan start", 17: "K3 first rows staged", 18: "K3 greedy pass", 19: "K3 outputs"}
-for grp in ((0, 8), (16, 20)):
+for grp in (((0, 12),) if fused else ((0, 8), (16, 20))):
     base = t[grp[0]]
     prev = base
     for i in range(grp[0], grp[1]):

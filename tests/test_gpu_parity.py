@@ -415,3 +415,32 @@ def test_full_size_config4_dense_crowd():
     got = ops.assign_targets(W.COCO_LEVELS, W.STRIDES, W.HISFCOS_RANGES, gt.to(DEV), labels.to(DEV), want_index=True)
     assert_equal_int(to_np(got[3]), to_np(want[3]), what="gt index")
     assert np.array_equal(to_np(got[2]), to_np(want[2]))
+
+
+# ------------------------------------------------------------------------------------------
+# fused K2+K3 kernel (class-bucketed sparse mask) against the dense three-kernel path
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ncls,crowded,seed,max_box", [(3, True, 51, 1000), (80, True, 52, 1000), (1, True, 53, 1000),
+                                                       (20, False, 54, 1024), (5, True, 55, 300)])
+def test_fused_postprocess_equals_dense_stage_chain(ncls, crowded, seed, max_box):
+    """Crowded boxes (many same-class overlaps) and large boxes around the top-left corner (negative
+    x1, y1: the cross-class 'wildcard' case of the coordinate trick).  The fused kernel must give
+    exactly what K1 -> K2 -> dense NMS (stand-alone entry) and the oracle give."""
+    x = W.head_outputs(2, ncls, W.VOC_LEVELS, seed=seed, crowded=crowded)
+    for lv in range(len(x[2])):
+        x[2][lv][:, :2, :3, :3] += 300.0           # l, t huge near the corner -> x1, y1 << -1 (wildcards)
+        x[0][lv][:, :, :3, :3] += 3.0              # and make sure those points are selected
+    xc = cuda_levels(x)
+    head = P.FCOSHead(0.05, 0.6, max_box, W.STRIDES)
+    s, c, b, n = head.detect(xc)
+    score, cls0 = ops.score_points(xc[0], xc[1], W.STRIDES)
+    ks, kc, kb, kp, kn = ops.select_topk(xc[2], W.STRIDES, score, cls0, 0.05, max_box)
+    ds, dc, db, dk, dn = ops.batched_nms(kb, ks, kc.long(), 0.05, 0.6, kn)
+    assert torch.equal(n, dn)
+    want = O.detect(x, 0.05, 0.6, max_box, W.STRIDES)
+    for i in range(2):
+        m = int(n[i])
+        assert torch.equal(s[i, :m], ds[i, :m]) and torch.equal(c[i, :m], dc[i, :m]) and torch.equal(b[i, :m], db[i, :m])
+        assert_detections_match((to_np(s[i, :m]), to_np(c[i, :m]), to_np(b[i, :m])),
+                                tuple(to_np(t) for t in want[i]), rel=REL_TOL, what=f"img {i}")
+    assert int((kb[..., 0] < -1).logical_and(kb[..., 1] < -1).sum()) > 0     # wildcards were present
