@@ -355,6 +355,8 @@ def main():
         fake = [torch.empty(TRAIN_BATCH, 1, h, w, device="meta") for h, w in W.COCO_LEVELS]
 
         def train_step(i):
+            for t in regs[i % 4]:
+                t.grad = None                              # optimizer.zero_grad(set_to_none=True)
             tgt = gen([[fake, fake, fake], gt, labels])
             loss = B.compute_reg_loss(regs[i % 4], tgt[2], None, "giou", _mask_src=tgt[1]).mean()
             loss.backward()
