@@ -177,81 +177,85 @@ def main():
     head = B.FCOSHead(SCORE_THR, NMS_THR, MAX_BOX, W.STRIDES)
     sampler = ClockSampler(local)
 
-    from pytorch_object_detection_b200 import sharding
-    gathered = {}
-
-    def gather(outs):
-        """The path's only collective: ONE all_gather of the shard's packed detections (scores, boxes,
-        classes, keep indices and counts share one allocation) into a preallocated [world, bytes] buffer."""
-        if dist is None:
-            return
-        key = outs[0].data_ptr()
-        if key not in gathered:
-            packed = sharding.packed_of(outs[0])
-            gathered[key] = (packed, packed.new_empty((world, packed.numel())))
-        packed, full = gathered[key]
-        return dist.all_gather_into_tensor(full, packed, async_op=True)   # runs on NCCL's stream
-
-    # One CUDA graph per input set: FCOSHead.detect (4 kernel launches) captured once, replayed per
-    # step, so the timed loop is not bound by Python/ctypes launch overhead.  The NCCL gather of the
-    # graph's static outputs runs eagerly after each replay.
+    # A "round" = one pass over the `sets` input batches = `sets` steps, captured as ONE CUDA graph so the
+    # timed loop is not bound by Python launch overhead.  Batches are independent, so inside the graph they
+    # are forked round-robin onto `streams` capture streams: K1 (HBM-bound, all SMs) of one batch overlaps
+    # the per-image select/NMS kernel (one CTA per image, latency-bound) of the others.
+    # Multi-GPU: the path's only collective is the final gather of the detections.  The packed outputs
+    # (scores, boxes, classes, keep indices, counts in one allocation) of a whole round sit in one buffer,
+    # so ONE NCCL all_gather serves `sets` steps; two rounds (A/B buffers) alternate so that the gather of
+    # one overlaps the kernels of the other.
+    k_out = min(MAX_BOX, P)
+    pk_bytes = ops.packed_nbytes(BATCH, k_out)
+    stage_big = torch.empty((pk_bytes,), dtype=torch.uint8, device=dev)
+    stage_full = torch.empty((world, pk_bytes), dtype=torch.uint8, device=dev) if world > 1 else None
     for hs in dev_sets:                                   # warm the allocator / library before capture
         head.detect(hs, clip_hw=W.COCO_HW)
     torch.cuda.synchronize()
-    graphs, graph_outs = [], []
-    for hs in dev_sets:
+
+    def capture_round(n_streams, count=None):
+        count = args.sets if count is None else count
+        out_big = torch.empty((count, pk_bytes), dtype=torch.uint8, device=dev)
+        side = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            outs = head.detect(hs, clip_hw=W.COCO_HW)
-        graphs.append(g)
-        graph_outs.append(outs)
+            cs = torch.cuda.current_stream()
+            for st in side:
+                st.wait_stream(cs)                        # fork
+            for s_i, hs in enumerate(dev_sets[:count]):
+                with torch.cuda.stream(side[s_i % n_streams]):
+                    head.detect(hs, clip_hw=W.COCO_HW, out_packed=out_big[s_i])
+            for st in side:
+                cs.wait_stream(st)                        # join
+        full = torch.empty((world, count * pk_bytes), dtype=torch.uint8, device=dev) if world > 1 else None
+        return g, out_big, full
 
-    # Batches are independent, so consecutive steps are issued round-robin on `--streams` CUDA streams:
-    # K1 (HBM-bound, all SMs) of one batch overlaps the per-image select/NMS kernel (one CTA per image,
-    # latency-bound) of the batches before it.  A graph's buffers are reused every `sets` steps, so a
-    # replay first waits (on the device) for the previous replay of the same graph and for its gather.
-    n_streams = max(1, min(args.streams, args.sets - 1))
-    streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
-    pending = [None] * args.sets                          # gather of set s still reading its outputs?
-    replayed = [None] * args.sets                         # event: last replay of graph s finished
+    def timed_rounds(n_streams):
+        rounds = [capture_round(n_streams) for _ in range(2)]      # A / B
+        n_rounds, tail = divmod(args.steps, args.sets)             # EXACTLY args.steps steps are timed
+        if tail:
+            rounds.append(capture_round(n_streams, tail))
+        pending = [None, None, None]
+        # rounds A and B are replayed on two different streams so that the tail of one round overlaps the
+        # head of the next (a replay of A still waits for the previous replay of A: same stream)
+        outer = [torch.cuda.Stream(device=dev) for _ in range(2 if n_streams > 1 else 1)]
+        done = [None, None, None]
 
-    def step(i, pipelined=True):
-        s = i % args.sets
-        st = streams[i % n_streams] if pipelined else torch.cuda.current_stream()
-        with torch.cuda.stream(st):
-            if replayed[s] is not None:
-                st.wait_event(replayed[s])
-            if pending[s] is not None:
-                pending[s].wait()                         # stream-level wait: outputs of set s are free again
-            graphs[s].replay()
-            ev = torch.cuda.Event()
-            ev.record(st)
-            replayed[s] = ev
-            pending[s] = gather(graph_outs[s])            # overlaps with the next steps' kernels
-        return graph_outs[s]
+        def run_round(r, which=None):
+            q = r % 2 if which is None else which
+            g, out_big, full = rounds[q]
+            with torch.cuda.stream(outer[q % len(outer)]):
+                if pending[q] is not None:
+                    pending[q].wait()                     # device-side: last gather of this buffer finished
+                g.replay()
+                if dist is not None:
+                    pending[q] = dist.all_gather_into_tensor(full, out_big.reshape(-1), async_op=True)
+                done[q] = torch.cuda.Event()
+                done[q].record()
 
-    def drain():
-        cur = torch.cuda.current_stream()
-        for s in range(args.sets):
-            if replayed[s] is not None:
-                cur.wait_event(replayed[s])
-            if pending[s] is not None:
-                pending[s].wait()
-                pending[s] = None
+        def drain():
+            cur = torch.cuda.current_stream()
+            for q in range(3):
+                if done[q] is not None:
+                    cur.wait_event(done[q])
+                if pending[q] is not None:
+                    pending[q].wait()
+                    pending[q] = None
 
-    def timed_steps(pipelined):
-        for i in range(warmup):
-            step(i, pipelined)
+        for r in range(max(2, -(-warmup // args.sets))):
+            run_round(r)
         drain()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with sampler:
             e0.record()
-            for st in streams:
+            for st in outer:
                 st.wait_event(e0)                         # nothing starts before the start event
-            for i in range(args.steps):
-                step(i, pipelined)
-            drain()                                       # the last steps and gathers are inside the timed region
+            for r in range(n_rounds):
+                run_round(r)
+            if tail:
+                run_round(0, which=2)
+            drain()                                       # the last gathers are inside the timed region
             e1.record()
             barrier()
         ms = e0.elapsed_time(e1)
@@ -259,13 +263,14 @@ def main():
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t[0])
-        return ms / args.steps
+        return ms / args.steps, args.steps
 
     # ---- value: device-resident, `n_streams` batches in flight; and one batch at a time ------------
-    ms_per_step = timed_steps(True)
+    n_streams = max(1, min(args.streams, args.sets))
+    ms_per_step, steps_timed = timed_rounds(n_streams)
     value = world * BATCH / (ms_per_step * 1e-3)
-    ms_single = timed_steps(False)
-    launches = args.steps * 2                             # score_points + fused select/NMS kernel per step
+    ms_single, _ = timed_rounds(1)
+    launches = steps_timed * 2                            # score_points + fused select/NMS kernel per step
 
     # ---- e2e: pinned host inputs -> H2D -> public API -> D2H of the detections -----------------
     pinned = [[[t.pin_memory() for t in part] for part in hs] for hs in host_sets[:2]]
@@ -273,11 +278,11 @@ def main():
     e2e_steps = max(3, min(args.steps, 30))
     d2h_bytes = 0
 
-    head.detect(stage, clip_hw=W.COCO_HW)
+    head.detect(stage, clip_hw=W.COCO_HW, out_packed=stage_big)
     torch.cuda.synchronize()
     g_stage = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g_stage):
-        stage_outs = head.detect(stage, clip_hw=W.COCO_HW)
+        stage_outs = head.detect(stage, clip_hw=W.COCO_HW, out_packed=stage_big)
 
     def e2e_step(i):
         nonlocal d2h_bytes
@@ -286,9 +291,8 @@ def main():
             for a, b in zip(ps, pd):
                 b.copy_(a, non_blocking=True)              # H2D of this step's head outputs
         g_stage.replay()
-        work = gather(stage_outs)
-        if work is not None:
-            work.wait()
+        if dist is not None:
+            dist.all_gather_into_tensor(stage_full, stage_big)
         res = [t.cpu() for t in stage_outs]                # blocking D2H of the step's detections
         d2h_bytes = sum(t.numel() * t.element_size() for t in res)
         return res
@@ -405,13 +409,13 @@ def main():
             dist.destroy_process_group()
         return
     cpu = cpu_reference_leg(steps=6, warmup=1, sample_images=4)
-    line = {"metric": "postprocess_throughput", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+    line = {"metric": "postprocess_throughput", "value": value, "unit": "img/s", "n_gpus": world, "steps": steps_timed,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH,
                        "l2": f"{args.sets} input sets of {in_bytes / 1e6:.0f} MB rotated (> 126 MB L2)",
-                       "in_flight": f"{n_streams} batches on {n_streams} CUDA streams (one CUDA graph per batch)",
-                       "collective": "one all_gather of the packed detections per step" if world > 1 else "none"},
+                       "in_flight": f"{n_streams} batches on {n_streams} CUDA streams inside one CUDA graph of {args.sets} steps",
+                       "collective": f"one all_gather of the packed detections per {args.sets} steps, overlapped" if world > 1 else "none"},
             "single_stream": {"value": world * BATCH / (ms_single * 1e-3), "unit": "img/s", "ms_per_step": ms_single},
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "steps": e2e_steps, "api": "FCOSHead.detect(clip_hw=...) on pinned host inputs"},

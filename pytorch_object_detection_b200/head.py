@@ -36,10 +36,15 @@ class FCOSHead(nn.Module):
         self.strides = strides
 
     # -- batched, padded contract (new: the reference cannot return ragged batches) ------------
-    def detect(self, x, clip_hw: Tuple[int, int] | None = None):
+    def detect(self, x, clip_hw: Tuple[int, int] | None = None, out_packed: Tensor | None = None):
         """x = (cls_list, cnt_list, reg_list).  Returns scores [B,K], classes [B,K] i64,
         boxes [B,K,4], counts [B] i32 (device tensors, no host sync); boxes are clipped to
-        ``clip_hw`` = (H, W) when given (ClipBoxes fused into the writer)."""
+        ``clip_hw`` = (H, W) when given (ClipBoxes fused into the writer).  ``out_packed`` places
+        the outputs in a caller-owned buffer (see ``ops.postprocess``)."""
+        if out_packed is not None:
+            s, c, b, _, n = ops.postprocess(x[0], x[1], x[2], self.strides, self.score, self.nms_threshold,
+                                            self.max_box, clip_hw, out_packed)
+            return s, c, b, n
         s, c, b, _, n = torch.ops.b200det.postprocess(
             list(x[0]), list(x[1]), list(x[2]), [int(v) for v in self.strides], float(self.score),
             float(self.nms_threshold), int(self.max_box), *((int(clip_hw[0]), int(clip_hw[1])) if clip_hw else (0, 0)))

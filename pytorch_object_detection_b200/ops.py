@@ -88,11 +88,14 @@ def _levels(cls: Sequence[Tensor] | None, cnt: Sequence[Tensor] | None, reg: Seq
 # inference
 # --------------------------------------------------------------------------------------------
 def postprocess(cls: Sequence[Tensor], cnt: Sequence[Tensor], reg: Sequence[Tensor], strides: Sequence[int],
-                score_thr: float, nms_thr: float, max_box: int, clip_hw: Tuple[int, int] | None = None):
+                score_thr: float, nms_thr: float, max_box: int, clip_hw: Tuple[int, int] | None = None,
+                out_packed: Tensor | None = None):
     """FCOSHead.forward (+ ClipBoxes) for any batch size, padded outputs.
 
     Returns scores [B,K] f32, classes [B,K] i64 (1-based), boxes [B,K,4] f32, keep [B,K] i64,
-    counts [B] i32 with K = min(max_box, P); rows beyond counts[b] are unspecified.
+    counts [B] i32 with K = min(max_box, P); rows beyond counts[b] are unspecified.  All five share
+    one allocation; ``out_packed`` (uint8, ``packed_nbytes(B, K)`` bytes, 256-byte aligned) lets the
+    caller place it, e.g. inside a buffer that one collective gathers for several batches.
     """
     lib = _lib.load()
     lv, keep_alive, p_total, batch, n = _levels(cls, cnt, reg, strides)
@@ -103,7 +106,11 @@ def postprocess(cls: Sequence[Tensor], cnt: Sequence[Tensor], reg: Sequence[Tens
     ncls = keep_alive[0].shape[1]
     ws_bytes = lib.b200det_postprocess_workspace_bytes(batch, p_total, k)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    scores, classes, boxes, keep, counts = detection_views(packed_detections(batch, k, dev), batch, k)
+    if out_packed is None:
+        out_packed = packed_detections(batch, k, dev)
+    elif out_packed.device != dev or out_packed.data_ptr() % 256:
+        raise _lib.B200DetError("out_packed must live on the inputs' device and be 256-byte aligned")
+    scores, classes, boxes, keep, counts = detection_views(out_packed, batch, k)
     ch, cw = (int(clip_hw[0]), int(clip_hw[1])) if clip_hw else (0, 0)
     with torch.cuda.device(dev):
         rc = lib.b200det_postprocess(lv, n, batch, ncls, float(score_thr), float(nms_thr), k, ch, cw,
@@ -122,6 +129,11 @@ def _packed_layout(batch: int, k: int):
         offs.append(off)
         off += (sz + 255) // 256 * 256
     return offs, sizes, off
+
+
+def packed_nbytes(batch: int, k: int) -> int:
+    """Bytes of the packed output buffer of a [batch, k] post-process call."""
+    return _packed_layout(batch, k)[2]
 
 
 def packed_detections(batch: int, k: int, device) -> Tensor:
