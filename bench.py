@@ -183,8 +183,8 @@ def main():
     # the per-image select/NMS kernel (one CTA per image, latency-bound) of the others.
     # Multi-GPU: the path's only collective is the final gather of the detections.  The packed outputs
     # (scores, boxes, classes, keep indices, counts in one allocation) of a whole round sit in one buffer,
-    # so ONE NCCL all_gather serves `sets` steps; two rounds (A/B buffers) alternate so that the gather of
-    # one overlaps the kernels of the other.
+    # so ONE NCCL all_gather serves `sets` steps; four output buffers rotate over two streams so that a
+    # gather overlaps the kernels of the following rounds and never delays the reuse of its buffer.
     k_out = min(MAX_BOX, P)
     pk_bytes = ops.packed_nbytes(BATCH, k_out)
     stage_big = torch.empty((pk_bytes,), dtype=torch.uint8, device=dev)
@@ -211,18 +211,19 @@ def main():
         return g, out_big, full
 
     def timed_rounds(n_streams):
-        rounds = [capture_round(n_streams) for _ in range(2)]      # A / B
+        n_buf = 4                                                  # output buffers (graphs) in rotation
+        rounds = [capture_round(n_streams) for _ in range(n_buf)]
         n_rounds, tail = divmod(args.steps, args.sets)             # EXACTLY args.steps steps are timed
         if tail:
             rounds.append(capture_round(n_streams, tail))
-        pending = [None, None, None]
+        pending = [None] * (n_buf + 1)
         # rounds A and B are replayed on two different streams so that the tail of one round overlaps the
         # head of the next (a replay of A still waits for the previous replay of A: same stream)
         outer = [torch.cuda.Stream(device=dev) for _ in range(2 if n_streams > 1 else 1)]
-        done = [None, None, None]
+        done = [None] * (n_buf + 1)
 
         def run_round(r, which=None):
-            q = r % 2 if which is None else which
+            q = r % n_buf if which is None else which
             g, out_big, full = rounds[q]
             with torch.cuda.stream(outer[q % len(outer)]):
                 if pending[q] is not None:
@@ -235,14 +236,14 @@ def main():
 
         def drain():
             cur = torch.cuda.current_stream()
-            for q in range(3):
+            for q in range(n_buf + 1):
                 if done[q] is not None:
                     cur.wait_event(done[q])
                 if pending[q] is not None:
                     pending[q].wait()
                     pending[q] = None
 
-        for r in range(max(2, -(-warmup // args.sets))):
+        for r in range(max(n_buf, -(-warmup // args.sets))):
             run_round(r)
         drain()
         barrier()
@@ -254,7 +255,7 @@ def main():
             for r in range(n_rounds):
                 run_round(r)
             if tail:
-                run_round(0, which=2)
+                run_round(0, which=n_buf)
             drain()                                       # the last gathers are inside the timed region
             e1.record()
             barrier()
