@@ -316,28 +316,27 @@ def main():
     # ---- roofline of the dominant kernel (K1) timed alone, same inputs, same rotation ----------
     peak, peak_src = peaks()
     k1_bytes = BATCH * P * ((NCLS + 1) * 4 + 4 + 2)       # cls + cnt planes read, score f32 + class i16 written
-    # K1 is launched through the same C-ABI entry the fused call uses; one CUDA graph per input set
-    # (a single kernel node each) so that the CUDA events bracket back-to-back launches, not Python.
-    k1_graphs = []
+    # K1 is launched through the same C-ABI entry the fused call uses.  One CUDA graph holds `chunk`
+    # back-to-back launches rotating over the input sets, so the CUDA events bracket kernel time, not
+    # Python or graph-launch latency.
     for hs in dev_sets:
         ops.score_points(hs[0], hs[1], W.STRIDES)
     torch.cuda.synchronize()
-    for hs in dev_sets:
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+    chunk = 2 * args.sets                                   # launches per graph replay / event pair
+    k1_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(k1_graph):
+        for i in range(chunk):
+            hs = dev_sets[i % args.sets]
             ops.score_points(hs[0], hs[1], W.STRIDES)
-        k1_graphs.append(g)
-    for i in range(warmup):
-        k1_graphs[i % args.sets].replay()
+    for i in range(max(1, warmup // chunk + 1)):
+        k1_graph.replay()
     torch.cuda.synchronize()
-    chunk = 10                                              # launches per event pair
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(max(1, args.steps // chunk))]
     with sampler:
-        for j, (a, b) in enumerate(evs):
+        for a, b in evs:
             a.record()
-            for i in range(chunk):
-                k1_graphs[(j * chunk + i) % args.sets].replay()
+            k1_graph.replay()
             b.record()
         torch.cuda.synchronize()
     k1_ms = sorted(a.elapsed_time(b) / chunk for a, b in evs)
