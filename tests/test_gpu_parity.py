@@ -444,3 +444,78 @@ def test_fused_postprocess_equals_dense_stage_chain(ncls, crowded, seed, max_box
         assert_detections_match((to_np(s[i, :m]), to_np(c[i, :m]), to_np(b[i, :m])),
                                 tuple(to_np(t) for t in want[i]), rel=REL_TOL, what=f"img {i}")
     assert int((kb[..., 0] < -1).logical_and(kb[..., 1] < -1).sum()) > 0     # wildcards were present
+
+
+# ------------------------------------------------------------------------------------------
+# input formats and the less-travelled paths of the head
+# ------------------------------------------------------------------------------------------
+def same_detections(got, ref):
+    """padded outputs: rows beyond counts[b] are unspecified, compare the valid prefix only"""
+    if not torch.equal(got[3], ref[3]):
+        return False
+    for i, n in enumerate(ref[3].tolist()):
+        if not all(torch.equal(a[i, :n], b[i, :n]) for a, b in zip(got[:3], ref[:3])):
+            return False
+    return True
+
+
+def test_head_accepts_half_and_channels_last_inputs():
+    x = W.head_outputs(2, 20, W.VOC_LEVELS, seed=61)
+    xc = cuda_levels(x)
+    head = P.FCOSHead(0.05, 0.6, 1000, W.STRIDES)
+    ref = head.detect(xc)
+    # channels_last (what cuDNN convolutions often return): same values, different strides
+    xl = [[t.contiguous(memory_format=torch.channels_last) for t in part] for part in xc]
+    assert not xl[0][0].is_contiguous()
+    got = head.detect(xl)
+    assert same_detections(got, ref)
+    # fp16 head outputs (AMP): evaluated in fp32 on the up-cast values
+    xh = [[t.half() for t in part] for part in xc]
+    got = head.detect(xh)
+    want = head.detect([[t.float() for t in part] for part in xh])
+    assert same_detections(got, want)
+
+
+@pytest.mark.parametrize("max_box,thr,nms_thr", [(2000, 0.05, 0.6), (1500, 0.0, 0.5), (1000, 0.05, -0.5),
+                                                 (10000, 0.05, 0.6), (1, 0.05, 0.6)])
+def test_head_large_k_and_odd_thresholds_match_oracle(max_box, thr, nms_thr):
+    """k > 1024 takes the three-kernel chain (per-class branch of batched_nms above 1000 candidates);
+    nms_thr < 0 (a zero IoU suppresses) takes the dense mask; k > P selects every point."""
+    x = W.head_outputs(2, 20, W.VOC_LEVELS, seed=62, crowded=True)
+    head = P.FCOSHead(thr, nms_thr, max_box, W.STRIDES)
+    s, c, b, n = head.detect(cuda_levels(x))
+    want = O.detect(x, thr, nms_thr, max_box, W.STRIDES)
+    for i in range(2):
+        m = int(n[i])
+        assert_detections_match((to_np(s[i, :m]), to_np(c[i, :m]), to_np(b[i, :m])),
+                                tuple(to_np(t) for t in want[i]), rel=REL_TOL, what=f"k={max_box} img {i}")
+
+
+def test_single_level_and_tiny_maps():
+    x = W.head_outputs(3, 7, [(5, 3)], seed=63)
+    head = P.FCOSHead(0.05, 0.6, 1000, [16])
+    s, c, b, n = head.detect(cuda_levels(x))
+    want = O.detect(x, 0.05, 0.6, 1000, [16])
+    for i in range(3):
+        m = int(n[i])
+        assert_detections_match((to_np(s[i, :m]), to_np(c[i, :m]), to_np(b[i, :m])),
+                                tuple(to_np(t) for t in want[i]), rel=REL_TOL, what=f"img {i}")
+    gt = torch.tensor([[[4.0, 4.0, 40.0, 70.0], [-1, -1, -1, -1]]] * 3)
+    lab = torch.tensor([[3, -1]] * 3)
+    got = ops.assign_targets([(5, 3)], [16], [[-1, 64]], gt.to(DEV), lab.to(DEV), want_index=True)
+    ref = O.assign_targets([(5, 3)], gt, lab, [16], [[-1, 64]])
+    assert_equal_int(to_np(got[0]), to_np(ref[0]), what="cls_t")
+    assert np.array_equal(to_np(got[2]), to_np(ref[2]))
+    assert_equal_int(to_np(got[3]), to_np(ref[3]), what="gt index")
+
+
+def test_assign_large_batch_tile_shape():
+    """B*P above the small/large tile switch (<128 threads x 8 points> kernel)."""
+    gt, labels = W.gt_boxes(80, 40, W.COCO_HW, 80, seed=64)
+    got = ops.assign_targets(W.COCO_LEVELS, W.STRIDES, W.HISFCOS_RANGES, gt.to(DEV), labels.to(DEV), want_index=True)
+    sel = [0, 17, 79]
+    ref = O.assign_targets(W.COCO_LEVELS, gt[sel], labels[sel], W.STRIDES, W.HISFCOS_RANGES)
+    for j, i in enumerate(sel):
+        assert_equal_int(to_np(got[0][i]), to_np(ref[0][j]), what="cls_t")
+        assert np.array_equal(to_np(got[2][i]), to_np(ref[2][j]))
+        assert_equal_int(to_np(got[3][i]), to_np(ref[3][j]), what="gt index")
