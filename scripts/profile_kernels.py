@@ -46,7 +46,12 @@ score, cls0 = ops.score_points(sets[0][0], sets[0][1], W.STRIDES)
 cand = ops.select_topk(sets[0][2], W.STRIDES, score, cls0, 0.05, 1000)
 npos = ops.box_loss_fwd(tsets[0][2], tgt[1], tgt[2], 1)[1]
 
+crowd = [W.crowd_candidates(5000, 80, seed=400 + i) for i in range(8)]
+cb = torch.stack([c[0] for c in crowd]).to(dev)
+cs = torch.stack([c[1] for c in crowd]).to(dev)
+cc = torch.stack([c[2] for c in crowd]).to(dev)
 cases = {
+    "nms_crowd5000_b8": lambda i: ops.batched_nms(cb, cs, cc, 0.05, 0.6),
     "score_points": lambda i: ops.score_points(sets[i % args.sets][0], sets[i % args.sets][1], W.STRIDES),
     "select_topk": lambda i: ops.select_topk(sets[0][2], W.STRIDES, score, cls0, 0.05, 1000),
     "batched_nms": lambda i: ops.batched_nms(cand[2], cand[0], cand[1].long(), 0.05, 0.6, cand[4]),
