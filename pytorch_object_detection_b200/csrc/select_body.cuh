@@ -106,6 +106,9 @@ __device__ __forceinline__ SelectResult select_topk_cta(const LevelTable& lt, co
   const int sort_cap = n2;    // the sort below handles up to n2 keys and orders ties by point index
   uint32_t T = kmin;          // count(key >= kmin) = n_valid
   int cntT = n_valid;
+  const int list_cap = max(n2, 2 * kSelThreads);   // entries the dynamic shared buffer holds
+  bool listed = false;        // selected entries already compacted into sortbuf[0, total)
+  int total = 0;
   if (n_valid > sort_cap) {
     const uint32_t diff = kmin ^ kmax;              // non-zero here unless all keys are equal
     const int top = diff ? 31 - __clz(diff) : -1;
@@ -114,7 +117,10 @@ __device__ __forceinline__ SelectResult select_topk_cta(const LevelTable& lt, co
     // known to be selected; the cntT - above keys inside [T, T + 2^(bit+1)) are still undecided.
     int above = 0, bit = top;
     bool done = false;
-    for (; bit >= 0 && cntT - above > kFinishMax; --bit) {
+    // (k <= 2048: stop as soon as everything >= T fits the 2048-entry list of phase B; larger k: stop
+    // when few keys are undecided and let the single-warp fallback finish.)
+    const bool list_mode = kk <= 2 * kSelThreads;
+    for (; bit >= 0 && (list_mode ? cntT > 2 * kSelThreads : cntT - above > kFinishMax); --bit) {
       const uint32_t cand = T | (1u << bit);
       int c = 0;
       FOR_KEYS(c += (kx >= cand) ? 1 : 0;)
@@ -128,8 +134,54 @@ __device__ __forceinline__ SelectResult select_topk_cta(const LevelTable& lt, co
       }
     }
     B200DET_STAMP(2);
-    // Phase B: the few undecided keys go to shared memory and ONE warp decides the remaining bits
-    // with warp reductions only (no block barrier per bit).
+    // Phase B (common case): few keys are still undecided and everything >= T fits the shared buffer.
+    // ONE compaction pass over the registers moves those entries (key, ~index) to shared memory; the
+    // remaining bits, the tie rule and the final selection then work on <= 2 entries per thread.
+    if (!done && bit >= 0 && cntT <= min(list_cap, 2 * kSelThreads)) {
+      int mine_l = 0;
+      FOR_KEYS(mine_l += (kx >= T) ? 1 : 0;)
+      int n_l;
+      int at_l = block_exclusive_scan(mine_l, s_scan, &n_l);              // n_l == cntT
+      FOR_KEYS(if (kx >= T) {
+        sortbuf[at_l++] = ((unsigned long long)kx << 32) | (unsigned long long)(0xffffffffu - (uint32_t)ix);
+      })
+      __syncthreads();
+      const unsigned long long eA = (tid < n_l) ? sortbuf[tid] : 0ull;
+      const unsigned long long eB = (tid + kSelThreads < n_l) ? sortbuf[tid + kSelThreads] : 0ull;
+      const uint32_t kA = (uint32_t)(eA >> 32), kB = (uint32_t)(eB >> 32);
+      for (; bit >= 0; --bit) {
+        const uint32_t cand = T | (1u << bit);
+        const int c = block_sum(((kA >= cand) ? 1 : 0) + ((kB >= cand) ? 1 : 0), s_red, phase);
+        if (c >= kk) {
+          T = cand;
+          cntT = c;
+          if (c <= sort_cap) break;
+        }
+      }
+      int idx_lim_l = 0x7fffffff;
+      if (cntT > sort_cap) {          // every bit decided and too many ties on T: lowest point indices win
+        const int iA = (int)(0xffffffffu - (uint32_t)eA), iB = (int)(0xffffffffu - (uint32_t)eB);
+        const int c_gt = block_sum(((kA > T) ? 1 : 0) + ((kB > T) ? 1 : 0), s_red, phase);
+        const int r = kk - c_gt;
+        int L = 0;
+        for (int ib = 31 - __clz(P); ib >= 0; --ib) {
+          const int cand = L | (1 << ib);
+          const int e = block_sum(((kA == T && iA < cand) ? 1 : 0) + ((kB == T && iB < cand) ? 1 : 0), s_red, phase);
+          if (e <= r) L = cand;
+        }
+        idx_lim_l = L;
+      }
+      const int iA = (int)(0xffffffffu - (uint32_t)eA), iB = (int)(0xffffffffu - (uint32_t)eB);
+      const bool sA = kA && (kA > T || (kA == T && iA < idx_lim_l));
+      const bool sB = kB && (kB > T || (kB == T && iB < idx_lim_l));
+      int at_s = block_exclusive_scan((sA ? 1 : 0) + (sB ? 1 : 0), s_scan, &total);   // its barriers order the reads above
+      if (sA) sortbuf[at_s++] = eA;
+      if (sB) sortbuf[at_s++] = eB;
+      listed = true;
+      done = true;
+    }
+    // Phase B (fallback when the list does not fit): the undecided keys go to shared memory and ONE
+    // warp decides the remaining bits with warp reductions only.
     if (!done && bit >= 0) {
       const uint32_t span_hi = (bit >= 31) ? 0u : (T >> (bit + 1));       // keys sharing T's bits above `bit`
       int mine_u = 0;
@@ -167,7 +219,7 @@ __device__ __forceinline__ SelectResult select_topk_cta(const LevelTable& lt, co
   // cntT = count(key >= T) >= kk.  If it exceeds the sort capacity every bit was decided: T is
   // exactly the k-th key and more ties sit on it than fit -> keep the lowest point indices.
   int idx_lim = 0x7fffffff;
-  if (cntT > sort_cap) {
+  if (!listed && cntT > sort_cap) {
     int c = 0;
     FOR_KEYS(c += (kx > T) ? 1 : 0;)
     const int c_gt = block_sum(c, s_red, phase);
@@ -184,13 +236,14 @@ __device__ __forceinline__ SelectResult select_topk_cta(const LevelTable& lt, co
   }
 
   // ---- compaction (order irrelevant: sorted next) ---------------------------------------
-  int mine = 0;
-  FOR_KEYS(mine += (kx > T || (kx == T && ix < idx_lim)) ? 1 : 0;)
-  int total;
-  int at = block_exclusive_scan(mine, s_scan, &total);    // kk <= total <= n2
-  FOR_KEYS(if (kx > T || (kx == T && ix < idx_lim)) {
-    sortbuf[at++] = ((unsigned long long)kx << 32) | (unsigned long long)(0xffffffffu - (uint32_t)ix);
-  })
+  if (!listed) {
+    int mine = 0;
+    FOR_KEYS(mine += (kx > T || (kx == T && ix < idx_lim)) ? 1 : 0;)
+    int at = block_exclusive_scan(mine, s_scan, &total);    // kk <= total <= n2
+    FOR_KEYS(if (kx > T || (kx == T && ix < idx_lim)) {
+      sortbuf[at++] = ((unsigned long long)kx << 32) | (unsigned long long)(0xffffffffu - (uint32_t)ix);
+    })
+  }
   B200DET_STAMP(4);
   const size_t o0 = (size_t)b * out.cap;
   float vmax = -CUDART_INF_F;
