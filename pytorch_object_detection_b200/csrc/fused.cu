@@ -112,6 +112,7 @@ fused_select_nms_kernel(const LevelTable lt, const float* __restrict__ score, co
     scls[tid] = mycls;
   }
   if (tid == 0) set.mode[b] = trick ? kModeTrick : kModeVanilla;
+  B200DET_STAMP(12);
   const float cmax = block_max((float)mycls, s_f);            // its barriers also order the zero-fill before the atomics
   bool mywild = false;
   if (tid < n) {
@@ -144,6 +145,7 @@ fused_select_nms_kernel(const LevelTable lt, const float* __restrict__ score, co
     ocls[slot] = mycls;
   }
   __syncthreads();
+  B200DET_STAMP(13);
   if (tid < n) {
     // same-class pairs: this candidate (row tid) against the later members of its class bucket;
     // wildcard pairs (trick branch): this candidate against every wildcard box of another class.

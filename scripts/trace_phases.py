@@ -23,7 +23,7 @@ torch.cuda.synchronize()
 t = [0] * 64
 import os as _os
 fused = _os.environ.get("B200DET_NO_FUSED") != "1"
-for name, lo, hi in ((("fused", 0, 12),) if fused else (("select", 0, 8), ("nms", 16, 20))):
+for name, lo, hi in ((("fused", 0, 14),) if fused else (("select", 0, 8), ("nms", 16, 20))):
     buf = (C.c_longlong * 64)()
     fn = getattr(lib, "b200det_debug_read_trace_" + name)
     fn.argtypes = [C.c_void_p, C.c_int]
@@ -31,11 +31,12 @@ for name, lo, hi in ((("fused", 0, 12),) if fused else (("select", 0, 8), ("nms"
     t[lo:hi] = list(buf)[lo:hi]
 names = {0: "K2 start", 1: "K2 keys loaded + min/max", 2: "K2 phase A (block passes)", 3: "K2 phase B (warp finish)",
          4: "K2 tie + compaction", 5: "K2 sort", 6: "K2 gather/decode", 7: "K2 nms boxes",
-         8: "F select done", 9: "F class-bucket sparse mask", 10: "F greedy pass", 11: "F outputs",
+         8: "F select done", 12: "F   zero-fill + stage", 13: "F   buckets built", 9: "F   pair tests", 10: "F greedy pass", 11: "F outputs",
          16: "K3 scan start", 17: "K3 first rows staged", 18: "K3 greedy pass", 19: "K3 outputs"}
-for grp in (((0, 12),) if fused else ((0, 8), (16, 20))):
+order = [0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 13, 9, 10, 11]
+for grp in (((0, 14),) if fused else ((0, 8), (16, 20))):
     base = t[grp[0]]
     prev = base
-    for i in range(grp[0], grp[1]):
+    for i in (order if fused else range(grp[0], grp[1])):
         print(f"{names[i]:32s} +{(t[i] - prev) / 1.965e3:8.2f} us   (t = {(t[i] - base) / 1.965e3:8.2f} us)")
         prev = t[i]
