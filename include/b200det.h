@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200DET_ABI_VERSION 2
+#define B200DET_ABI_VERSION 3
 #define B200DET_MAX_LEVELS 8
 #define B200DET_MAX_BOX 8192      /* largest max_detection_box / NMS candidate count per image */
 
@@ -159,6 +159,40 @@ int b200det_cls_loss_fwd(const b200det_level* levels, int n_levels, int batch, i
 int b200det_cls_loss_bwd(const b200det_level* levels, float* const* grads, int n_levels, int batch,
                          int num_classes, const int64_t* cls_t,
                          const float* grad_loss, const float* num_pos, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4 fused: one launch per training step for
+ *   FCOSGenTargets.forward (head.py:218-316)
+ *   + compute_reg_loss forward AND its autograd backward (loss.py:116-177)
+ *   + compute_cnt_loss forward AND backward (loss.py:29-57; optional)
+ *   + the `.mean()` over the batch of FCOSLoss.forward (loss.py:210-213).
+ * One thread-block cluster per image; the assignment stays in shared memory, so the targets are
+ * written once and never re-read, and predictions are fetched at positives only.
+ *   levels[l].reg (+ .cnt when cnt_grads != NULL), h, w, stride : head outputs (read at positives)
+ *   reg_grads[l] [B,4,h,w], cnt_grads[l] [B,1,h,w] (host arrays of device pointers; cnt_grads may be
+ *     NULL together with cnt_loss): receive d(sum_b grad_*[b] * loss[b]) / d(map), zeros off positives
+ *   grad_box / grad_cnt [B] f32 device, or NULL for 1/B each (the gradient of the batch mean)
+ *   cls_t / cnt_t / reg_t : the targets, as b200det_assign_targets writes them (bit-identical)
+ *   box_loss / cnt_loss / num_pos [B] f32 : as b200det_box_loss_fwd / b200det_cnt_loss_fwd
+ *   mean_out [2] f32 or NULL : batch means of box_loss and cnt_loss, added in image order
+ *   workspace : b200det_assign_loss_workspace_bytes() bytes, ZERO before the first launch that uses
+ *     it (the kernel leaves it zero); one workspace per stream that may run this concurrently.
+ * ------------------------------------------------------------------------------------- */
+size_t b200det_assign_loss_workspace_bytes(void);
+int b200det_assign_loss_fused(const b200det_level* levels, float* const* reg_grads, float* const* cnt_grads,
+                              int n_levels, const float* limit_lo, const float* limit_hi,
+                              const float* radius_px, int batch, int max_gt,
+                              const float* gt_boxes, const int64_t* gt_labels, int mode,
+                              const float* grad_box, const float* grad_cnt,
+                              int64_t* cls_t, float* cnt_t, float* reg_t,
+                              float* box_loss, float* cnt_loss, float* num_pos, float* mean_out,
+                              void* workspace, void* stream);
+
+/* maps[i] (device, numel[i] floats) *= *factors[i] (device scalar) for i < n_maps <= 16; the arrays
+ * themselves are HOST arrays.  A map whose factor is exactly 1 is not touched.  This is the autograd
+ * backward of the fused step: its gradients are final unless the upstream gradient differs from 1. */
+int b200det_scale_maps(float* const* maps, const int64_t* numel, const float* const* factors, int n_maps,
+                       void* stream);
 
 #ifdef __cplusplus
 }

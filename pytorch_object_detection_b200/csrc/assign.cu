@@ -14,7 +14,7 @@
 // The kernel is a pure, fully coalesced write stream: 28 (+4) bytes per point, nothing re-read.
 // (A positive box with area >= 99999999 px^2 would lose to the reference's sentinel; images are
 // far smaller than 10^4 x 10^4, so that case is not modelled.)
-#include "common.cuh"
+#include "assign_body.cuh"
 
 B200DET_TRACE_BUFFER(assign)
 #ifdef B200DET_TRACE
@@ -37,13 +37,6 @@ struct AssignTable {
 // per-CTA prologue, so they get wide CTAs with short tiles; large batches get more, leaner CTAs.
 // Measured on B200 (28 B written per point): <256,4> 7.2 us at B=32; <128,8> 5.0 TB/s at B=128.
 constexpr long long kAssignSmallPoints = 1500000;   // B*P below this -> <256,4>
-
-struct GtEntry {
-  float x0, y0, x1, y1;
-  float cx, cy;          // (x0+x1)/2, (y0+y1)/2 as the reference rounds them (head.py:276-277)
-  int idx;
-  int label;             // class label (fits int32), staged so the epilogue has no dependent global load
-};
 
 template <int kAssignThreads, int kAssignPts>
 __global__ void __launch_bounds__(kAssignThreads, 768 / kAssignThreads)
@@ -68,36 +61,23 @@ assign_targets_kernel(const AssignTable at, const int M, const float* __restrict
   const int t0 = (tile - at.tile_off[l]) * kAssignTile;
   const int t1 = min(t0 + kAssignTile, hw) - 1;
   const float lo = at.lo[l], hi = at.hi[l], radius = at.radius[l];
-  const int half = s / 2;
-  const float sf = (float)s, halff = (float)half;
 
   const bool traced = blockIdx.x == 0 && (tile == 0 || tile == (int)gridDim.y - 1);
   const int tslot = tile == 0 ? 0 : 8;
   B200DET_STAMP_IF(traced, tslot + 0);
   if (threadIdx.x == 0) s_n = 0;
 #pragma unroll
-  for (int q = 0; q < kAssignPts; ++q) keys[threadIdx.x + q * kAssignThreads] = ~0ull;
+  for (int q = 0; q < kAssignPts; ++q) keys[threadIdx.x + q * kAssignThreads] = kNoWinner;
   __syncthreads();
   {
-    // Stage the image's boxes; keep the indices of those that can be positive somewhere in this tile.
-    // Conservative, rounding-safe pre-filter (margins of 1 px dwarf any fp32 rounding at image scale):
-    //  * rows covered by this tile -> y range; the centre mask needs |y - cy| < radius;
-    //  * a point strictly inside a box has max(l,t,r,b) in [max(w,h)/2, max(w,h)), so the level's
-    //    (lo, hi] range can only be met when max(w,h) > lo and max(w,h)/2 <= hi;
-    //  * side > 0 drops the -1 padding rows: a point cannot be strictly inside a degenerate box.
-    const float ymin = (float)((t0 / w) * s + half) - radius - 1.0f;
-    const float ymax = (float)((t1 / w) * s + half) + radius + 1.0f;
+    // Stage the image's boxes; keep the indices of those that can be positive somewhere in this tile
+    // (gt_may_hit: a conservative, rounding-safe pre-filter on rows, level range and padding rows).
     const float4* g4 = reinterpret_cast<const float4*>(gt_boxes) + (size_t)b * M;
     const long long* lab = gt_labels + (size_t)b * M;
     for (int m = threadIdx.x; m < M; m += kAssignThreads) {
-      const float4 g = g4[m];
-      const int label = (int)lab[m];
-      const float cx = __fmul_rn(__fadd_rn(g.x, g.z), 0.5f);
-      const float cy = __fmul_rn(__fadd_rn(g.y, g.w), 0.5f);
-      const float side = fmaxf(g.z - g.x, g.w - g.y);
-      gts[m] = GtEntry{g.x, g.y, g.z, g.w, cx, cy, m, label};
-      if (cy >= ymin && cy <= ymax && side > 0.f && side > lo - 1.0f && 0.5f * side <= hi + 1.0f)
-        cand[atomicAdd(&s_n, 1)] = m;
+      const GtEntry g = make_gt_entry(g4[m], m, (int)lab[m]);
+      gts[m] = g;
+      if (gt_may_hit(g, t0 / w, t1 / w, s, lo, hi, radius)) cand[atomicAdd(&s_n, 1)] = m;
     }
   }
   __syncthreads();
@@ -110,28 +90,11 @@ assign_targets_kernel(const AssignTable at, const int M, const float* __restrict
   // one cell of slack).  Every (box, window point) pair evaluates the reference's exact fp32
   // expressions; positives race with a 64-bit atomicMin on (area, GT index): smallest area, lowest
   // index on ties = torch.min's first index on the masked areas (head.py:285-286).
-  const int hwin = (int)ceilf(0.5f + radius / sf);
-  const int wside = 2 * hwin + 1, wcount = wside * wside;
+  const int hwin = window_half(radius, s);
+  const int wcount = (2 * hwin + 1) * (2 * hwin + 1);
   for (int pi = threadIdx.x; pi < n_list * wcount; pi += kAssignThreads) {
     const int e = pi / wcount, k = pi - e * wcount;
-    const GtEntry g = gts[cand[e]];
-    const int j = (int)floorf(g.cx / sf) + (k % wside) - hwin;
-    const int i = (int)floorf(g.cy / sf) + (k / wside) - hwin;
-    if (j < 0 || j >= w || i < 0 || i >= h) continue;
-    const int pos = i * w + j;
-    if (pos < t0 || pos > t1) continue;
-    const float x = (float)(j * s + half), y = (float)(i * s + half);
-    // max(x-cx, y-cy, cx-x, cy-y) = max(|x-cx|, |y-cy|) exactly (fp32 subtraction is odd-symmetric)
-    const float cmax = fmaxf(fabsf(__fsub_rn(x, g.cx)), fabsf(__fsub_rn(y, g.cy)));
-    if (!(cmax < radius)) continue;
-    const float lf = __fsub_rn(x, g.x0), tf = __fsub_rn(y, g.y0);
-    const float rf = __fsub_rn(g.x1, x), bf = __fsub_rn(g.y1, y);
-    const float omin = fminf(fminf(lf, tf), fminf(rf, bf));
-    const float omax = fmaxf(fmaxf(lf, tf), fmaxf(rf, bf));
-    if ((omin > 0.f) && (omax > lo) && (omax <= hi)) {
-      const float area = __fmul_rn(__fadd_rn(lf, rf), __fadd_rn(tf, bf));        // > 0: bits are monotone
-      atomicMin(&keys[pos - t0], ((unsigned long long)__float_as_uint(area) << 32) | (unsigned)g.idx);
-    }
+    window_vote(gts[cand[e]], k, hwin, s, w, h, t0, t1, lo, hi, radius, keys);
   }
   __syncthreads();
 
@@ -149,14 +112,10 @@ assign_targets_kernel(const AssignTable at, const int M, const float* __restrict
       float cnt = -1.f;
       float4 reg = make_float4(-1.f, -1.f, -1.f, -1.f);
       int best_m = -1;
-      if (key != ~0ull) {
+      if (key != kNoWinner) {
         best_m = (int)(unsigned)(key & 0xffffffffull);
         const GtEntry g = gts[best_m];
-        const float x = (float)(col * s + half), y = (float)(row * s + half);
-        reg = make_float4(__fsub_rn(x, g.x0), __fsub_rn(y, g.y0), __fsub_rn(g.x1, x), __fsub_rn(g.y1, y));
-        const float lr_min = fminf(reg.x, reg.z), lr_max = fmaxf(reg.x, reg.z);
-        const float tb_min = fminf(reg.y, reg.w), tb_max = fmaxf(reg.y, reg.w);
-        cnt = __fsqrt_rn(__fdiv_rn(__fmul_rn(lr_min, tb_min), __fadd_rn(__fmul_rn(lr_max, tb_max), 1e-10f)));
+        positive_targets(g, col, row, s, &reg, &cnt);
         label = (long long)g.label;
       }
       const size_t o = out0 + pos;
@@ -170,7 +129,6 @@ assign_targets_kernel(const AssignTable at, const int M, const float* __restrict
     if (col >= w) { col -= w; ++row; }
   }
   B200DET_STAMP_IF(traced, tslot + 2);
-  (void)halff;
 }
 
 }  // namespace

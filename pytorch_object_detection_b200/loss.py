@@ -149,3 +149,86 @@ class FCOSLoss(nn.Module):
         reg_loss = compute_reg_loss(reg_logit, reg_target, mask_pos, self.mode, _mask_src=src).mean()
         total_loss = cls_loss + cnt_loss + reg_loss
         return cls_loss, cnt_loss, reg_loss, total_loss
+
+
+class _FusedTargetLoss(torch.autograd.Function):
+    """Targets + box / centerness losses + their gradients from one kernel (csrc/train_fused.cu).
+
+    forward computes the gradients of the two batch means eagerly; backward only rescales them when the
+    upstream gradients differ from 1 (a no-op launch otherwise).  backward may run once per forward."""
+
+    @staticmethod
+    def forward(ctx, gt_boxes: Tensor, labels: Tensor, cfg, *maps: Tensor):
+        strides, limit_range, mode, radius, n_reg = cfg
+        reg, cnt = maps[:n_reg], (maps[n_reg:] or None)
+        r = ops.assign_loss_fused(reg, cnt, strides, limit_range, gt_boxes, labels, mode, radius)
+        ctx.n_reg, ctx.has_cnt = n_reg, cnt is not None
+        ctx.dtypes = [t.dtype for t in maps]
+        ctx.save_for_backward(*r["reg_grads"], *(r["cnt_grads"] or []))
+        ctx.set_materialize_grads(False)
+        mean = r["mean"]
+        aux = [r["cls_t"], r["cnt_t"], r["reg_t"], r["box_loss"], r["num_pos"]] + ([r["cnt_loss"]] if cnt else [])
+        ctx.mark_non_differentiable(*aux)
+        return (mean[0], mean[1], *aux)
+
+    @staticmethod
+    def backward(ctx, g_box, g_cnt, *_):
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("the fused target/loss step supports a single backward per forward")
+        ctx.consumed = True
+        grads = list(ctx.saved_tensors)
+        n = ctx.n_reg
+        todo, factors = [], []
+        for i, g in enumerate(grads):
+            up = g_box if i < n else g_cnt
+            if up is None:
+                grads[i] = None
+            else:
+                todo.append(g)
+                factors.append(up.detach().to(torch.float32).reshape(()))
+        if todo:
+            ops.scale_maps_(todo, factors)
+        out = [g if g is None else g.to(dt) for g, dt in zip(grads, ctx.dtypes)]
+        return (None, None, None, *out)
+
+
+class FCOSTargetLoss(nn.Module):
+    """``FCOSGenTargets`` (head.py:211-316) followed by ``FCOSLoss`` (loss.py:196-215) as ONE module.
+
+    ``forward([out, gt_boxes, labels])`` takes what the reference hands to ``FCOSGenTargets`` and returns
+    what its ``FCOSLoss`` returns, ``(cls_loss, cnt_loss, reg_loss, total_loss)``; the targets of the step
+    are kept in ``self.targets`` as ``(cls_t [B,P,1] i64, cnt_t [B,P,1], reg_t [B,P,4])``.  Target
+    assignment, the box and centerness losses and their gradients are one kernel launch; the focal loss
+    is one forward and one backward kernel.
+    """
+
+    def __init__(self, strides: Sequence[int], limit_range: Sequence[Sequence[float]], mode: str = "giou",
+                 sample_radio_ratio: float = 1.5):
+        super().__init__()
+        assert len(strides) == len(limit_range)                          # head.py:216
+        if mode not in _MODES:
+            raise NotImplementedError("reg loss only implemented ['iou','giou']")   # loss.py:137-138
+        self.strides = [int(s) for s in strides]
+        self.limit_range = [tuple(float(v) for v in r) for r in limit_range]
+        self.mode = mode
+        self.sample_radio_ratio = float(sample_radio_ratio)
+        self.targets = None
+
+    def box_cnt_losses(self, cnt_logits, reg_preds, gt_boxes: Tensor, labels: Tensor):
+        """(reg_loss, cnt_loss) batch means + targets; ``cnt_logits`` may be None (box loss only)."""
+        n = min(len(self.strides), len(reg_preds), len(cnt_logits) if cnt_logits is not None else len(reg_preds))
+        cfg = (self.strides[:n], self.limit_range[:n], _MODES[self.mode], self.sample_radio_ratio, n)
+        maps = list(reg_preds[:n]) + (list(cnt_logits[:n]) if cnt_logits is not None else [])
+        out = _FusedTargetLoss.apply(gt_boxes, labels, cfg, *maps)
+        self.targets = (out[2], out[3], out[4])
+        self.per_image = {"reg": out[5], "num_pos": out[6], "cnt": out[7] if cnt_logits is not None else None}
+        return out[0], (out[1] if cnt_logits is not None else None)
+
+    def forward(self, x):
+        (cls_logits, cnt_logits, reg_preds), gt_boxes, labels = x
+        assert len(cls_logits) >= 1 and len(cnt_logits) == len(cls_logits) == len(reg_preds)
+        reg_loss, cnt_loss = self.box_cnt_losses(cnt_logits, reg_preds, gt_boxes, labels)
+        cls_t, cnt_t, _ = self.targets
+        cls_loss = compute_cls_loss(cls_logits, cls_t, None, _mask_src=cnt_t).mean()
+        total_loss = cls_loss + cnt_loss + reg_loss
+        return cls_loss, cnt_loss, reg_loss, total_loss

@@ -23,7 +23,7 @@ launch_count = 0          # kernels launched through this module (bench.py repor
 # kernels per C entry point (see csrc/*.cu)
 _LAUNCHES = {"postprocess": 4, "batched_nms": 3, "score_points": 1, "select_topk": 1, "clip_boxes": 1,
              "assign_targets": 1, "box_loss_fwd": 1, "box_loss_bwd": 1, "cnt_loss_fwd": 1, "cnt_loss_bwd": 1,
-             "cls_loss_fwd": 2, "cls_loss_bwd": 1}
+             "cls_loss_fwd": 2, "cls_loss_bwd": 1, "assign_loss_fused": 1, "scale_maps": 1}
 
 
 def _count(name: str) -> None:
@@ -399,6 +399,95 @@ def cls_loss_bwd(cls: Sequence[Tensor], cls_t: Tensor, grad_loss: Tensor, npos: 
     _lib.check(rc, "b200det_cls_loss_bwd")
     _count("cls_loss_bwd")
     return grads
+
+
+# --------------------------------------------------------------------------------------------
+# fused training step: targets + box / centerness loss forward and backward in one launch
+# --------------------------------------------------------------------------------------------
+_fused_ws = {}            # device index -> zeroed ticket buffer (the kernel leaves it zero)
+
+
+def _fused_workspace(dev: torch.device) -> Tensor:
+    lib = _lib.load()
+    n = int(lib.b200det_assign_loss_workspace_bytes())
+    if torch.cuda.is_current_stream_capturing():
+        ws = _fused_ws.get(dev.index)
+        return ws if ws is not None else torch.zeros(n, dtype=torch.uint8, device=dev)
+    if dev.index not in _fused_ws:
+        _fused_ws[dev.index] = torch.zeros(n, dtype=torch.uint8, device=dev)
+    return _fused_ws[dev.index]
+
+
+def assign_loss_fused(reg: Sequence[Tensor], cnt: Sequence[Tensor] | None, strides: Sequence[int],
+                      limit_range: Sequence[Sequence[float]], gt_boxes: Tensor, labels: Tensor, mode: int,
+                      sample_radius: float = 1.5, grad_box: Tensor | None = None, grad_cnt: Tensor | None = None,
+                      want_mean: bool = True, workspace: Tensor | None = None):
+    """FCOSGenTargets.forward + compute_reg_loss (+ compute_cnt_loss) forward AND backward, one kernel.
+
+    Returns a dict: cls_t [B,P,1] i64, cnt_t [B,P,1], reg_t [B,P,4] (bit-identical to assign_targets),
+    box_loss / cnt_loss / num_pos [B], mean [2] (batch means of box_loss, cnt_loss), reg_grads /
+    cnt_grads (lists shaped like the maps) = gradient of sum_b grad_*[b] * loss[b]; grad_* default to
+    1/B, i.e. the gradient of the batch mean.  Concurrent calls on different streams of one device need
+    their own zero-initialised ``workspace`` (b200det_assign_loss_workspace_bytes() bytes).
+    """
+    lib = _lib.load()
+    lv, keep_alive, p_total, batch, n = _levels(None, cnt, reg, strides)
+    if len(limit_range) < n:
+        raise _lib.B200DetError("limit_range is shorter than the level list")
+    _need_cuda(gt_boxes, "gt_boxes")
+    _need_cuda(labels, "labels")
+    dev = keep_alive[0].device
+    gt = _f32c(gt_boxes, "gt_boxes")
+    lab = labels.to(torch.int64).contiguous()
+    if gt.dim() != 3 or gt.shape[-1] != 4 or lab.shape != gt.shape[:2] or gt.shape[0] != batch:
+        raise _lib.B200DetError("expected gt_boxes [B,M,4] and labels [B,M] with the maps' batch size")
+    m = lab.shape[1]
+    lo_arr = (C.c_float * n)(*[float(r[0]) for r in limit_range[:n]])
+    hi_arr = (C.c_float * n)(*[float(r[1]) for r in limit_range[:n]])
+    ra_arr = (C.c_float * n)(*[float(s * sample_radius) for s in list(strides)[:n]])
+    per = 2 if cnt is not None else 1
+    maps_cnt = keep_alive[0::per][:n] if cnt is not None else None      # _levels appends (cnt, reg) per level
+    maps_reg = keep_alive[1::per][:n] if cnt is not None else keep_alive[:n]
+    reg_grads = [torch.empty_like(x) for x in maps_reg]
+    cnt_grads = [torch.empty_like(x) for x in maps_cnt] if cnt is not None else None
+    cls_t = torch.empty((batch, p_total, 1), dtype=torch.int64, device=dev)
+    cnt_t = torch.empty((batch, p_total, 1), dtype=torch.float32, device=dev)
+    reg_t = torch.empty((batch, p_total, 4), dtype=torch.float32, device=dev)
+    box_loss = torch.empty((batch,), dtype=torch.float32, device=dev)
+    cnt_loss = torch.empty_like(box_loss) if cnt is not None else None
+    num_pos = torch.empty_like(box_loss)
+    mean = torch.empty((2,), dtype=torch.float32, device=dev) if want_mean else None
+    ws = workspace if workspace is not None else (_fused_workspace(dev) if want_mean else None)
+    gb = _f32c(grad_box, "grad_box").reshape(batch) if grad_box is not None else None
+    gc = _f32c(grad_cnt, "grad_cnt").reshape(batch) if grad_cnt is not None else None
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    with torch.cuda.device(dev):
+        rc = lib.b200det_assign_loss_fused(lv, _grad_ptrs(reg_grads), _grad_ptrs(cnt_grads) if cnt_grads else None, n,
+                                           lo_arr, hi_arr, ra_arr, batch, m, gt.data_ptr(), lab.data_ptr(), int(mode),
+                                           ptr(gb), ptr(gc), cls_t.data_ptr(), cnt_t.data_ptr(), reg_t.data_ptr(),
+                                           box_loss.data_ptr(), ptr(cnt_loss), num_pos.data_ptr(), ptr(mean), ptr(ws),
+                                           _stream(gt))
+    _lib.check(rc, "b200det_assign_loss_fused")
+    _count("assign_loss_fused")
+    return {"cls_t": cls_t, "cnt_t": cnt_t, "reg_t": reg_t, "box_loss": box_loss, "cnt_loss": cnt_loss,
+            "num_pos": num_pos, "mean": mean, "reg_grads": reg_grads, "cnt_grads": cnt_grads}
+
+
+def scale_maps_(maps: Sequence[Tensor], factors: Sequence[Tensor]) -> None:
+    """maps[i] *= factors[i] (0-dim fp32 CUDA tensors) in one launch; a factor of exactly 1 touches nothing."""
+    lib = _lib.load()
+    n = len(maps)
+    assert n == len(factors) and n > 0
+    for t, f in zip(maps, factors):
+        _need_cuda(t, "map")
+        assert t.dtype == torch.float32 and t.is_contiguous() and f.dtype == torch.float32 and f.numel() == 1
+    m_arr = (C.c_void_p * n)(*[t.data_ptr() for t in maps])
+    n_arr = (C.c_int64 * n)(*[t.numel() for t in maps])
+    f_arr = (C.c_void_p * n)(*[f.data_ptr() for f in factors])
+    with torch.cuda.device(maps[0].device):
+        rc = lib.b200det_scale_maps(m_arr, n_arr, f_arr, n, _stream(maps[0]))
+    _lib.check(rc, "b200det_scale_maps")
+    _count("scale_maps")
 
 
 # --------------------------------------------------------------------------------------------

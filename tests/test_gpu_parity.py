@@ -373,6 +373,114 @@ def test_box_loss_tie_subgradients_match_autograd():
 
 
 # ------------------------------------------------------------------------------------------
+# K4 fused: targets + box / centerness loss forward and backward in one launch
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(TRAIN_CASES))
+@pytest.mark.parametrize("mode", ["giou", "iou"])
+def test_fused_target_loss_matches_reference(name, mode):
+    """FCOSTargetLoss([out, gt, labels]) == FCOSLoss([out, FCOSGenTargets(...)]) of the reference (golden)."""
+    g, x, gt, labels, ranges, levels = train_case(name)
+    xc = cuda_levels(x)
+    for part in xc:
+        for t in part:
+            t.requires_grad_(True)
+    step = P.FCOSTargetLoss(W.STRIDES, ranges, mode)
+    losses = step([xc, gt.to(DEV), labels.to(DEV)])
+    cls_t, cnt_t, reg_t = step.targets
+    assert_equal_int(to_np(cls_t), g["cls_t"], what="cls_t")
+    assert np.array_equal(to_np(reg_t), g["reg_t"]), "reg_t not bit-exact"
+    assert_cnt_matches(cnt_t, g["cnt_t"], g["reg_t"])
+    assert all(v.dim() == 0 for v in losses)
+    assert_close([float(v) for v in losses], g[f"loss_{mode}"], rel=REL_TOL, what=f"loss {mode}")
+    losses[3].backward()
+    for lv in range(len(levels)):
+        assert_close(to_np(xc[2][lv].grad), g[f"g_reg_{mode}_{lv}"], rel=REL_TOL, abs_=1e-9, what=f"g_reg {lv}")
+        assert_close(to_np(xc[1][lv].grad), g[f"g_cnt_{mode}_{lv}"], rel=REL_TOL, abs_=1e-9, what=f"g_cnt {lv}")
+
+
+def test_fused_target_loss_equals_unfused_kernels_full_size_and_upstream_scale():
+    """Config 3 at full size: the fused launch against the separate assign / loss kernels — targets
+    bit-identical, losses and gradients to 1e-5 — with a non-unit upstream gradient (loss scaling),
+    with and without the centerness branch, repeated so the self-resetting ticket is exercised."""
+    B, M = 32, 100
+    gt, labels = W.gt_boxes(B, M, W.COCO_HW, 80, seed=411)
+    gt, labels = gt.to(DEV), labels.to(DEV)
+    gen = torch.Generator().manual_seed(412)
+    reg = [torch.exp(torch.randn(B, 4, h, w, generator=gen) + 3).to(DEV).requires_grad_(True) for h, w in W.COCO_LEVELS]
+    cnt = [torch.randn(B, 1, h, w, generator=gen).to(DEV).requires_grad_(True) for h, w in W.COCO_LEVELS]
+    want_t = ops.assign_targets(W.COCO_LEVELS, W.STRIDES, W.HISFCOS_RANGES, gt, labels)
+    want_reg = P.compute_reg_loss(reg, want_t[2], None, "giou", _mask_src=want_t[1])
+    want_cnt = P.compute_cnt_loss(cnt, want_t[1], None, _mask_src=want_t[1])
+    (3.0 * want_reg.mean() + 0.5 * want_cnt.mean()).backward()
+    want_g = [t.grad.clone() for t in reg + cnt]
+    step = P.FCOSTargetLoss(W.STRIDES, W.HISFCOS_RANGES, "giou")
+    for rep in range(3):
+        for t in reg + cnt:
+            t.grad = None
+        reg_loss, cnt_loss = step.box_cnt_losses(cnt, reg, gt, labels)
+        for a, b in zip(step.targets, want_t):
+            assert torch.equal(a, b)
+        assert_close(to_np(step.per_image["reg"]), to_np(want_reg), rel=REL_TOL)
+        assert_close(to_np(step.per_image["cnt"]), to_np(want_cnt), rel=REL_TOL)
+        assert_close(float(reg_loss), float(want_reg.mean()), rel=REL_TOL)
+        assert_close(float(cnt_loss), float(want_cnt.mean()), rel=REL_TOL)
+        (3.0 * reg_loss + 0.5 * cnt_loss).backward()
+        for t, w in zip(reg + cnt, want_g):
+            assert_close(to_np(t.grad), to_np(w), rel=REL_TOL, abs_=1e-10)
+    # box loss only (no centerness maps), unit upstream
+    for t in reg:
+        t.grad = None
+    reg_only, none = step.box_cnt_losses(None, reg, gt, labels)
+    assert none is None
+    reg_only.backward()
+    for t, w in zip(reg, want_g[:5]):
+        assert_close(to_np(t.grad), to_np(w) / 3.0, rel=REL_TOL, abs_=1e-10)
+
+
+def test_fused_target_loss_edge_cases():
+    """No GT at all, M = 0, one image, a slice-boundary-heavy tiny pyramid, dense crowd (300 GT)."""
+    step = P.FCOSTargetLoss(W.STRIDES, W.FCOS_RANGES, "giou")
+    gen = torch.Generator().manual_seed(5)
+
+    def maps(b, levels):
+        reg = [torch.exp(torch.randn(b, 4, h, w, generator=gen) + 2).to(DEV).requires_grad_(True) for h, w in levels]
+        cnt = [torch.randn(b, 1, h, w, generator=gen).to(DEV).requires_grad_(True) for h, w in levels]
+        return reg, cnt
+
+    def check(levels, gt, labels, ranges=W.FCOS_RANGES):
+        st = P.FCOSTargetLoss(W.STRIDES[:len(levels)], ranges[:len(levels)], "giou")
+        reg, cnt = maps(gt.shape[0], levels)
+        a, c = st.box_cnt_losses(cnt, reg, gt.to(DEV), labels.to(DEV))
+        (a + c).backward()
+        got_g = [t.grad.clone() for t in reg + cnt]
+        for t in reg + cnt:
+            t.grad = None
+        want_t = ops.assign_targets(levels, W.STRIDES[:len(levels)], ranges[:len(levels)], gt.to(DEV), labels.to(DEV))
+        wr = P.compute_reg_loss(reg, want_t[2], None, "giou", _mask_src=want_t[1]).mean()
+        wc = P.compute_cnt_loss(cnt, want_t[1], None, _mask_src=want_t[1]).mean()
+        (wr + wc).backward()
+        for x, y in zip(st.targets, want_t):
+            assert torch.equal(x, y)
+        assert_close(float(a), float(wr), rel=REL_TOL, abs_=1e-12)
+        assert_close(float(c), float(wc), rel=REL_TOL, abs_=1e-12)
+        for t, w in zip(reg + cnt, got_g):
+            assert_close(to_np(w), to_np(t.grad), rel=REL_TOL, abs_=1e-10)
+        return st
+
+    # all padding rows
+    check(W.VOC_LEVELS, torch.full((2, 3, 4), -1.0), torch.full((2, 3), -1, dtype=torch.int64))
+    # M = 0
+    st = check(W.VOC_LEVELS, torch.zeros((2, 0, 4)), torch.zeros((2, 0), dtype=torch.int64))
+    assert float(st.per_image["num_pos"].max()) == 1.0
+    # batch 1, tiny pyramid whose levels are smaller than a slice (several levels per CTA, empty CTAs)
+    gt, labels = W.gt_boxes(1, 6, (64, 96), 5, seed=77)
+    check([(8, 12), (4, 6), (2, 3), (1, 2), (1, 1)], gt, labels)
+    # dense crowd: BASELINE config 4's assignment side
+    gt, labels = W.gt_boxes(4, 300, W.COCO_HW, 80, seed=78)
+    check(W.COCO_LEVELS, gt, labels, W.HISFCOS_RANGES)
+
+
+# ------------------------------------------------------------------------------------------
 # full-size configs: properties that do not need the oracle at scale + oracle spot checks
 # ------------------------------------------------------------------------------------------
 def test_full_size_config2_postprocess_properties_and_oracle():
