@@ -166,8 +166,10 @@ int b200det_cls_loss_bwd(const b200det_level* levels, float* const* grads, int n
  *   + compute_reg_loss forward AND its autograd backward (loss.py:116-177)
  *   + compute_cnt_loss forward AND backward (loss.py:29-57; optional)
  *   + the `.mean()` over the batch of FCOSLoss.forward (loss.py:210-213).
- * One thread-block cluster per image; the assignment stays in shared memory, so the targets are
- * written once and never re-read, and predictions are fetched at positives only.
+ * Three launches chained by programmatic dependent launch: a per-image count of the positives
+ * (num_pos scales every gradient), one streaming kernel in which the assignment never leaves shared
+ * memory (targets written once and never re-read, predictions fetched at positives only), and a
+ * one-CTA deterministic reduction of the loss partials.
  *   levels[l].reg (+ .cnt when cnt_grads != NULL), h, w, stride : head outputs (read at positives)
  *   reg_grads[l] [B,4,h,w], cnt_grads[l] [B,1,h,w] (host arrays of device pointers; cnt_grads may be
  *     NULL together with cnt_loss): receive d(sum_b grad_*[b] * loss[b]) / d(map), zeros off positives
@@ -175,10 +177,10 @@ int b200det_cls_loss_bwd(const b200det_level* levels, float* const* grads, int n
  *   cls_t / cnt_t / reg_t : the targets, as b200det_assign_targets writes them (bit-identical)
  *   box_loss / cnt_loss / num_pos [B] f32 : as b200det_box_loss_fwd / b200det_cnt_loss_fwd
  *   mean_out [2] f32 or NULL : batch means of box_loss and cnt_loss, added in image order
- *   workspace : b200det_assign_loss_workspace_bytes() bytes, ZERO before the first launch that uses
- *     it (the kernel leaves it zero); one workspace per stream that may run this concurrently.
+ *   workspace : b200det_assign_loss_workspace_bytes(batch, P) bytes (tile partials); one workspace per
+ *     stream that may run this concurrently.
  * ------------------------------------------------------------------------------------- */
-size_t b200det_assign_loss_workspace_bytes(void);
+size_t b200det_assign_loss_workspace_bytes(int batch, int num_points);
 int b200det_assign_loss_fused(const b200det_level* levels, float* const* reg_grads, float* const* cnt_grads,
                               int n_levels, const float* limit_lo, const float* limit_hi,
                               const float* radius_px, int batch, int max_gt,
@@ -186,7 +188,7 @@ int b200det_assign_loss_fused(const b200det_level* levels, float* const* reg_gra
                               const float* grad_box, const float* grad_cnt,
                               int64_t* cls_t, float* cnt_t, float* reg_t,
                               float* box_loss, float* cnt_loss, float* num_pos, float* mean_out,
-                              void* workspace, void* stream);
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* maps[i] (device, numel[i] floats) *= *factors[i] (device scalar) for i < n_maps <= 16; the arrays
  * themselves are HOST arrays.  A map whose factor is exactly 1 is not touched.  This is the autograd

@@ -18,7 +18,7 @@ SOURCES = ["api.cu", "score.cu", "select.cu", "nms.cu", "fused.cu", "assign.cu",
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-prec-div=true",
+    "-prec-div=true", "-diag-suppress", "177",
     "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC,-O2,-Wall",
     "-shared", "-cudart", "static",

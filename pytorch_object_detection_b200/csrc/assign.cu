@@ -26,13 +26,6 @@ B200DET_TRACE_BUFFER(assign)
 namespace b200det {
 namespace {
 
-struct AssignTable {
-  int h[B200DET_MAX_LEVELS], w[B200DET_MAX_LEVELS], stride[B200DET_MAX_LEVELS], hw[B200DET_MAX_LEVELS];
-  int point_off[B200DET_MAX_LEVELS + 1], tile_off[B200DET_MAX_LEVELS + 1];
-  float lo[B200DET_MAX_LEVELS], hi[B200DET_MAX_LEVELS], radius[B200DET_MAX_LEVELS];
-  int n_levels, num_points;
-};
-
 // Tile shape (threads x points per thread), chosen per launch: small batches are dominated by the
 // per-CTA prologue, so they get wide CTAs with short tiles; large batches get more, leaner CTAs.
 // Measured on B200 (28 B written per point): <256,4> 7.2 us at B=32; <128,8> 5.0 TB/s at B=128.
@@ -151,28 +144,9 @@ extern "C" int b200det_assign_targets(const int32_t* level_hw, const int32_t* st
   const bool small = (long long)batch * total_points < kAssignSmallPoints;
   const int tile_points = small ? 256 * 4 : 128 * 8;
   AssignTable at;
-  long long off = 0;
-  int toff = 0;
-  for (int l = 0; l < B200DET_MAX_LEVELS; ++l) {
-    const bool on = l < n_levels;
-    if (on && (level_hw[2 * l] <= 0 || level_hw[2 * l + 1] <= 0 || strides[l] <= 0)) return B200DET_ERR_ARG;
-    at.h[l] = on ? level_hw[2 * l] : 0;
-    at.w[l] = on ? level_hw[2 * l + 1] : 0;
-    at.stride[l] = on ? strides[l] : 0;
-    at.hw[l] = at.h[l] * at.w[l];
-    at.lo[l] = on ? limit_lo[l] : 0.f;
-    at.hi[l] = on ? limit_hi[l] : 0.f;
-    at.radius[l] = on ? radius_px[l] : 0.f;
-    at.point_off[l] = (int)off;
-    at.tile_off[l] = toff;
-    off += at.hw[l];
-    toff += (at.hw[l] + tile_points - 1) / tile_points;
-    if (off > (1ll << 30)) return B200DET_ERR_ARG;
-  }
-  at.point_off[B200DET_MAX_LEVELS] = (int)off;
-  at.tile_off[B200DET_MAX_LEVELS] = toff;
-  at.n_levels = n_levels;
-  at.num_points = (int)off;
+  if (!make_assign_table(level_hw, strides, limit_lo, limit_hi, radius_px, n_levels, tile_points, &at))
+    return B200DET_ERR_ARG;
+  const int toff = at.tile_off[B200DET_MAX_LEVELS];
   if (toff > 65535) return B200DET_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto launch = [&](auto kernel, int threads) -> int {

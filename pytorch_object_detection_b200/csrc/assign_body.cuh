@@ -12,6 +12,43 @@
 
 namespace b200det {
 
+// Level geometry of one launch (kernel parameter, by value).
+struct AssignTable {
+  int h[B200DET_MAX_LEVELS], w[B200DET_MAX_LEVELS], stride[B200DET_MAX_LEVELS], hw[B200DET_MAX_LEVELS];
+  int point_off[B200DET_MAX_LEVELS + 1], tile_off[B200DET_MAX_LEVELS + 1];
+  float lo[B200DET_MAX_LEVELS], hi[B200DET_MAX_LEVELS], radius[B200DET_MAX_LEVELS];
+  int n_levels, num_points;
+};
+
+// Fills the table; tiles are `tile_points` consecutive points of one level.  Returns false on bad sizes.
+inline bool make_assign_table(const int32_t* level_hw, const int32_t* strides, const float* limit_lo,
+                              const float* limit_hi, const float* radius_px, int n_levels, int tile_points,
+                              AssignTable* at) {
+  long long off = 0;
+  int toff = 0;
+  for (int l = 0; l < B200DET_MAX_LEVELS; ++l) {
+    const bool on = l < n_levels;
+    if (on && (level_hw[2 * l] <= 0 || level_hw[2 * l + 1] <= 0 || strides[l] <= 0)) return false;
+    at->h[l] = on ? level_hw[2 * l] : 0;
+    at->w[l] = on ? level_hw[2 * l + 1] : 0;
+    at->stride[l] = on ? strides[l] : 0;
+    at->hw[l] = at->h[l] * at->w[l];
+    at->lo[l] = on ? limit_lo[l] : 0.f;
+    at->hi[l] = on ? limit_hi[l] : 0.f;
+    at->radius[l] = on ? radius_px[l] : 0.f;
+    at->point_off[l] = (int)off;
+    at->tile_off[l] = toff;
+    off += at->hw[l];
+    toff += (at->hw[l] + tile_points - 1) / tile_points;
+    if (off > (1ll << 30)) return false;
+  }
+  at->point_off[B200DET_MAX_LEVELS] = (int)off;
+  at->tile_off[B200DET_MAX_LEVELS] = toff;
+  at->n_levels = n_levels;
+  at->num_points = (int)off;
+  return true;
+}
+
 struct GtEntry {
   float x0, y0, x1, y1;
   float cx, cy;          // (x0+x1)/2, (y0+y1)/2 as the reference rounds them (head.py:276-277)
@@ -49,32 +86,42 @@ __device__ __forceinline__ int window_half(const float radius, const int s) {
   return (int)ceilf(0.5f + radius / (float)s);
 }
 
-// One (box, window point k) pair: evaluates the reference's exact fp32 expressions and, when the point
-// lies in [t0, t1] of this level and is positive for the box, votes with a 64-bit atomicMin on
-// (area bits, GT index): smallest area, lowest index on ties.  keys is indexed by pos - t0.
-__device__ __forceinline__ void window_vote(const GtEntry& g, const int k, const int hwin, const int s, const int w,
-                                            const int h, const int t0, const int t1, const float lo, const float hi,
-                                            const float radius, unsigned long long* keys) {
+// One (box, window point k) pair: evaluates the reference's exact fp32 expressions.  Returns true when
+// the window point exists in the level and is positive for the box; *pos = its row-major index in the
+// level, *area = (l+r)*(t+b) (> 0, so its bit pattern is monotone).
+__device__ __forceinline__ bool window_point_positive(const GtEntry& g, const int k, const int hwin, const int s,
+                                                      const int w, const int h, const float lo, const float hi,
+                                                      const float radius, int* pos, float* area) {
   const int wside = 2 * hwin + 1;
   const int half = s / 2;
   const float sf = (float)s;
   const int j = (int)floorf(g.cx / sf) + (k % wside) - hwin;
   const int i = (int)floorf(g.cy / sf) + (k / wside) - hwin;
-  if (j < 0 || j >= w || i < 0 || i >= h) return;
-  const int pos = i * w + j;
-  if (pos < t0 || pos > t1) return;
+  if (j < 0 || j >= w || i < 0 || i >= h) return false;
   const float x = (float)(j * s + half), y = (float)(i * s + half);
   // max(x-cx, y-cy, cx-x, cy-y) = max(|x-cx|, |y-cy|) exactly (fp32 subtraction is odd-symmetric)
   const float cmax = fmaxf(fabsf(__fsub_rn(x, g.cx)), fabsf(__fsub_rn(y, g.cy)));
-  if (!(cmax < radius)) return;
+  if (!(cmax < radius)) return false;
   const float lf = __fsub_rn(x, g.x0), tf = __fsub_rn(y, g.y0);
   const float rf = __fsub_rn(g.x1, x), bf = __fsub_rn(g.y1, y);
   const float omin = fminf(fminf(lf, tf), fminf(rf, bf));
   const float omax = fmaxf(fmaxf(lf, tf), fmaxf(rf, bf));
-  if ((omin > 0.f) && (omax > lo) && (omax <= hi)) {
-    const float area = __fmul_rn(__fadd_rn(lf, rf), __fadd_rn(tf, bf));        // > 0: bits are monotone
-    atomicMin(&keys[pos - t0], ((unsigned long long)__float_as_uint(area) << 32) | (unsigned)g.idx);
-  }
+  if (!((omin > 0.f) && (omax > lo) && (omax <= hi))) return false;
+  *pos = i * w + j;
+  *area = __fmul_rn(__fadd_rn(lf, rf), __fadd_rn(tf, bf));
+  return true;
+}
+
+// The vote of a positive pair whose point lies in [t0, t1] of this level: a 64-bit atomicMin on
+// (area bits, GT index) = smallest area, lowest index on ties.  keys is indexed by pos - t0.
+__device__ __forceinline__ void window_vote(const GtEntry& g, const int k, const int hwin, const int s, const int w,
+                                            const int h, const int t0, const int t1, const float lo, const float hi,
+                                            const float radius, unsigned long long* keys) {
+  int pos;
+  float area;
+  if (!window_point_positive(g, k, hwin, s, w, h, lo, hi, radius, &pos, &area)) return;
+  if (pos < t0 || pos > t1) return;
+  atomicMin(&keys[pos - t0], ((unsigned long long)__float_as_uint(area) << 32) | (unsigned)g.idx);
 }
 
 // Targets of a positive point (col, row) of a level with this stride, assigned to box g.

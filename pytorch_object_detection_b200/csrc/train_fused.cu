@@ -1,24 +1,32 @@
-// K4 fused — target assignment + box (IoU / GIoU) loss + centerness BCE loss, forward AND backward,
-// in ONE launch.  Replaces, for one training step,
+// K4 fused — target assignment + box (IoU / GIoU) loss + centerness BCE loss, forward AND backward.
+// Replaces, for one training step,
 //   FCOSGenTargets.forward            model/modules/head.py:218-316
 //   compute_reg_loss (+ giou / iou)   model/loss.py:116-177      and its autograd backward
 //   compute_cnt_loss                  model/loss.py:29-57        and its autograd backward
 //   the two `.mean()` of FCOSLoss     model/loss.py:210-213
 //
-// One thread-block CLUSTER per image; CTA `rank` owns a contiguous slice of the image's level-major
-// points.  Phases (all data dependent state stays in shared memory, nothing is re-read from HBM):
-//   1. stage the image's GT boxes; list the (box, level) pairs that can be positive in the slice;
-//   2. box-centric vote (assign_body.cuh): per point a 64-bit atomicMin on (area, GT index);
-//   3. count the slice's positives, exchange the counts through distributed shared memory,
-//      cluster barrier -> every CTA knows num_pos of the image, hence the gradient scale;
-//   4. stream pass A: every point's targets (28 B) and the zero gradients of negatives (20 B) — the
-//      write stream starts here and keeps HBM busy while
-//      pass B fetches the predictions at the positives only, evaluates the loss terms and writes
-//      their gradients, already scaled by grad_loss[b] / num_pos[b];
-//   5. loss partials meet in CTA 0 through DSMEM and are added in rank order (deterministic);
-//      the last cluster to finish (self-resetting ticket) adds the per-image losses in image order
-//      and writes the two batch means.
+// The gradient of a positive carries 1 / num_pos of its image, so num_pos must be known before the
+// single streaming pass can write final gradients.  Three launches chained by programmatic dependent
+// launch (each starts while its predecessor runs and waits only where it needs the predecessor's result):
+//   count_positives_kernel  one cluster of 8 CTAs per image; a warp expands a (box, level) pair, its lanes
+//                           the window points; positives set a bit in the image's bitmap, held in the
+//                           shared memory of the cluster's CTA 0 (32-bit atomicOr over distributed shared
+//                           memory); popcount -> num_pos.  ~4 us of latency, hidden behind:
+//   assign_loss_tile_kernel a CTA owns 1024 points of one level of one image (the tiling of assign.cu):
+//                           stage the GT boxes, box-centric vote into shared memory, then ONE write
+//                           stream: every point's targets (28 B) and gradients (20 B; zeros off the
+//                           positives).  Predictions are fetched at positives only (all of a thread's
+//                           loads in flight together); loss terms and unscaled gradients are evaluated
+//                           before the wait for num_pos, only the scaling and the stores come after it.
+//   finalize_losses_kernel  one CTA: tile partials added in tile order, per-image losses in image order
+//                           (deterministic), batch means.
+// Nothing is re-read from HBM: the assignment never leaves shared memory.
 // HBM traffic: 48 B written per point + ~36 B read per positive; GT boxes are read once per CTA.
+// Measured (B200, config 3: B=32, P=23265, M<=100): 16.9 us for the three launches against 26.6 us for
+// assign + box-loss forward + backward as separate kernels (scripts/time_fused.py).
+// Tried and dropped: one cluster per image doing everything (the cluster barrier is a GPU-scope fence
+// that waits for the CTA's streaming stores to drain; 64-bit atomicMin over distributed shared memory is
+// not atomic against the local CAS loop) and in-kernel tickets for the final reduction (5 us tail).
 #include <cooperative_groups.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,226 +34,295 @@
 #include "assign_body.cuh"
 #include "loss_terms.cuh"
 
+B200DET_TRACE_BUFFER(train)
+
 namespace cg = cooperative_groups;
 
 namespace b200det {
 namespace {
 
-struct FusedTable {
+struct LossMaps {
   const float* reg[B200DET_MAX_LEVELS];
   const float* cnt[B200DET_MAX_LEVELS];
   float* greg[B200DET_MAX_LEVELS];
   float* gcnt[B200DET_MAX_LEVELS];
-  int h[B200DET_MAX_LEVELS], w[B200DET_MAX_LEVELS], stride[B200DET_MAX_LEVELS], hw[B200DET_MAX_LEVELS];
-  int point_off[B200DET_MAX_LEVELS + 1];
-  float lo[B200DET_MAX_LEVELS], hi[B200DET_MAX_LEVELS], radius[B200DET_MAX_LEVELS];
-  int n_levels, num_points;
-  int chunk;             // points per CTA = ceil(P / cluster size)
-  int has_cnt;           // centerness maps + gradients present
 };
 
-__device__ __forceinline__ int level_of(const FusedTable& t, const int p) {
-  int l = 0;
-#pragma unroll
-  for (int i = 1; i < B200DET_MAX_LEVELS; ++i) l += (i < t.n_levels && p >= t.point_off[i]) ? 1 : 0;
-  return l;
-}
-
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-constexpr int kMaxCluster = 16;
+// ---- num_pos[b] = clamp(#points of image b with at least one positive box, 1) ------------------------
+// One cluster of kCountSlices CTAs per image.  The (box, level) pairs of the image are dealt to the CTAs;
+// one thread tests one pair against the level-range / padding pre-filter, survivors go to a shared list
+// which the warps expand round-robin, lanes = window points.  A positive point sets its bit in the
+// image's bitmap, which lives in the shared memory of CTA 0 of the cluster (32-bit atomicOr through
+// distributed shared memory); after the cluster barrier CTA 0 popcounts it.
+constexpr int kCountSlices = 8;
+constexpr int kCountThreads = 256;
 
-template <int kThreads>
-__global__ void __launch_bounds__(kThreads)
-assign_loss_fused_kernel(const FusedTable ft, const int M, const float* __restrict__ gt_boxes,
-                         const long long* __restrict__ gt_labels, const int mode,
-                         const float* __restrict__ grad_box, const float* __restrict__ grad_cnt,
-                         const float inv_batch, long long* __restrict__ cls_t, float* __restrict__ cnt_t,
-                         float* __restrict__ reg_t, float* __restrict__ box_loss, float* __restrict__ cnt_loss,
-                         float* __restrict__ num_pos, float* __restrict__ mean_out, unsigned* __restrict__ ticket) {
+__global__ void __cluster_dims__(kCountSlices, 1, 1) __launch_bounds__(kCountThreads)
+count_positives_kernel(const AssignTable at, const int M, const float* __restrict__ gt_boxes,
+                       float* __restrict__ num_pos) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);          // [chunk] per own point
-  GtEntry* gts = reinterpret_cast<GtEntry*>(smem_raw + (size_t)ft.chunk * 8);          // [M] by GT index
-  int* cand = reinterpret_cast<int*>(gts + M);                                         // [M * levels] (level << 24) | m
+  GtEntry* gts = reinterpret_cast<GtEntry*>(smem_raw);                                      // [M]
+  unsigned* bitmap = reinterpret_cast<unsigned*>(smem_raw + (size_t)M * sizeof(GtEntry));   // [ceil(P / 32)], CTA 0's is used
   __shared__ float s_red[32];
-  __shared__ int s_count[kMaxCluster];          // positives per CTA of the cluster (every CTA holds a copy)
-  __shared__ float s_part[2 * kMaxCluster];     // loss partials (meaningful in CTA 0)
-  __shared__ int s_n;
-
+  __shared__ int s_list[kCountThreads];
+  __shared__ int s_list_n;
+  pdl_launch_dependents();                       // the streaming kernel may start; it waits before reading num_pos
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int csize = (int)cluster.num_blocks();
-  const int b = blockIdx.y;
-  const int P = ft.num_points;
-  const int p_lo = min(P, rank * ft.chunk), p_hi = min(P, p_lo + ft.chunk);
-  const int n_own = p_hi - p_lo;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int words = (at.num_points + 31) / 32;
+  if (rank == 0)
+    for (int i = tid; i < words; i += kCountThreads) bitmap[i] = 0u;
+  const float4* g4 = reinterpret_cast<const float4*>(gt_boxes) + (size_t)b * M;
+  for (int m = tid; m < M; m += kCountThreads) gts[m] = make_gt_entry(g4[m], m, 0);
+  cluster.sync();                                // CTA 0's bitmap is clear; every CTA of the cluster runs
+  unsigned* image_bits = cluster.map_shared_rank(bitmap, 0);
+
+  // This CTA's pairs are q = rank, rank + kCountSlices, ... (levels and boxes mix evenly).
+  const int lane = tid & 31, warp = tid >> 5;
+  const int n_pairs = M * at.n_levels;
+  for (int q0 = 0; q0 < n_pairs; q0 += kCountSlices * kCountThreads) {
+    __syncthreads();
+    if (tid == 0) s_list_n = 0;
+    __syncthreads();
+    const int q = q0 + tid * kCountSlices + rank;
+    if (q < n_pairs) {
+      const int l = q / M, m = q - l * M;
+      const float side = fmaxf(gts[m].x1 - gts[m].x0, gts[m].y1 - gts[m].y0);   // pre-filter of gt_may_hit
+      if (side > 0.f && side > at.lo[l] - 1.0f && 0.5f * side <= at.hi[l] + 1.0f)
+        s_list[atomicAdd(&s_list_n, 1)] = q;
+    }
+    __syncthreads();
+    const int n_list = s_list_n;
+    for (int e = warp; e < n_list; e += kCountThreads / 32) {
+      const int pair = s_list[e];
+      const int l = pair / M, m = pair - l * M;
+      const GtEntry g = gts[m];
+      const int s = at.stride[l];
+      const float radius = at.radius[l];
+      const int hwin = window_half(radius, s);
+      const int wcount = (2 * hwin + 1) * (2 * hwin + 1);
+      for (int k = lane; k < wcount; k += 32) {
+        int pos;
+        float area;
+        if (window_point_positive(g, k, hwin, s, at.w[l], at.h[l], at.lo[l], at.hi[l], radius, &pos, &area)) {
+          const int p = at.point_off[l] + pos;
+          atomicOr(image_bits + (p >> 5), 1u << (p & 31));
+        }
+      }
+    }
+  }
+  cluster.sync();                                // every vote has landed in CTA 0
+  if (rank != 0) return;
+  int c = 0;
+  for (int i = tid; i < words; i += kCountThreads) c += __popc(bitmap[i]);
+  const float total = block_sum_f((float)c, s_red);             // <= P < 2^24: exact in fp32
+  if (tid == 0) num_pos[b] = fmaxf(total, 1.f);
+}
+
+// ---- the streaming kernel -----------------------------------------------------------------------------
+constexpr int kTrainThreads = 256;
+
+constexpr int kTrainPts = 4;                  // 8 points per thread spills at the 64 registers 4 CTAs / SM allow
+constexpr int kTrainTile = kTrainThreads * kTrainPts;
+
+__global__ void __launch_bounds__(kTrainThreads, 3)
+assign_loss_tile_kernel(const AssignTable at, const LossMaps lm, const int has_cnt, const int M,
+                        const float* __restrict__ gt_boxes, const long long* __restrict__ gt_labels, const int mode,
+                        const float* __restrict__ grad_box, const float* __restrict__ grad_cnt, const float inv_batch,
+                        const float* num_pos, long long* __restrict__ cls_t, float* __restrict__ cnt_t,
+                        float* __restrict__ reg_t, float* partial, const int use_pdl) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GtEntry* gts = reinterpret_cast<GtEntry*>(smem_raw);                   // [M] the image's boxes, by GT index
+  int* cand = reinterpret_cast<int*>(smem_raw + (size_t)M * sizeof(GtEntry));   // [M] GT indices relevant to this tile
+  __shared__ unsigned long long keys[kTrainTile];                        // per point: (area bits << 32) | GT index
+  __shared__ float s_red[32];
+  __shared__ int s_n;
+
+  // grid = (image, tile), tile order reversed (coarse levels first), as in assign.cu
+  const int b = blockIdx.x;
+  const int n_tiles = (int)gridDim.y;
+  const int tile = n_tiles - 1 - (int)blockIdx.y;
   const int tid = threadIdx.x;
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < B200DET_MAX_LEVELS; ++i) l += (i < at.n_levels && tile >= at.tile_off[i]) ? 1 : 0;
+  const int hw = at.hw[l], w = at.w[l], h = at.h[l], s = at.stride[l];
+  const int t0 = (tile - at.tile_off[l]) * kTrainTile;
+  const int t1 = min(t0 + kTrainTile, hw) - 1;
+  const float lo = at.lo[l], hi = at.hi[l], radius = at.radius[l];
+  const float* __restrict__ reg_p = lm.reg[l] + (size_t)b * 4 * hw;
+  const float* __restrict__ cnt_p = has_cnt ? lm.cnt[l] + (size_t)b * hw : nullptr;
+  float* __restrict__ greg = lm.greg[l] + (size_t)b * 4 * hw;
+  float* __restrict__ gcnt = has_cnt ? lm.gcnt[l] + (size_t)b * hw : nullptr;
+  const bool traced = b == 0 && (tile == 0 || tile == n_tiles - 1);
+  const int tslot = tile == 0 ? 0 : 16;
+  B200DET_STAMP_IF(traced, tslot + 0);
+  if (use_pdl) pdl_launch_dependents();          // finalize_losses_kernel may become resident; it waits for this grid
 
-  cluster.barrier_arrive();      // matched by barrier_wait() before the first distributed-shared-memory store:
-                                 // by then every CTA of the cluster has started
-
-  // ---- 1. stage the boxes, list the (box, level) pairs relevant to the slice -----------------------
   if (tid == 0) s_n = 0;
-  for (int i = tid; i < n_own; i += kThreads) keys[i] = kNoWinner;
+#pragma unroll
+  for (int q = 0; q < kTrainPts; ++q) keys[tid + q * kTrainThreads] = kNoWinner;
+  __syncthreads();
   {
     const float4* g4 = reinterpret_cast<const float4*>(gt_boxes) + (size_t)b * M;
     const long long* lab = gt_labels + (size_t)b * M;
-    for (int m = tid; m < M; m += kThreads) gts[m] = make_gt_entry(g4[m], m, (int)lab[m]);
-  }
-  __syncthreads();
-  const int l_first = n_own > 0 ? level_of(ft, p_lo) : 0;
-  const int l_last = n_own > 0 ? level_of(ft, p_hi - 1) : -1;
-  int wmax = 1;                                   // window points per box, max over the slice's levels
-  for (int l = l_first; l <= l_last; ++l) {
-    const int side = 2 * window_half(ft.radius[l], ft.stride[l]) + 1;
-    wmax = max(wmax, side * side);
-  }
-  for (int i = tid; i < M * (l_last - l_first + 1); i += kThreads) {
-    const int l = l_first + i / M, m = i - (l - l_first) * M;
-    const int t0 = max(p_lo, ft.point_off[l]) - ft.point_off[l];
-    const int t1 = min(p_hi, ft.point_off[l + 1]) - 1 - ft.point_off[l];
-    const int w = ft.w[l];
-    if (gt_may_hit(gts[m], t0 / w, t1 / w, ft.stride[l], ft.lo[l], ft.hi[l], ft.radius[l]))
-      cand[atomicAdd(&s_n, 1)] = (l << 24) | m;
+    for (int m = tid; m < M; m += kTrainThreads) {
+      const GtEntry g = make_gt_entry(g4[m], m, (int)lab[m]);
+      gts[m] = g;
+      if (gt_may_hit(g, t0 / w, t1 / w, s, lo, hi, radius)) cand[atomicAdd(&s_n, 1)] = m;
+    }
   }
   __syncthreads();
   const int n_list = s_n;
-
-  // ---- 2. box-centric vote ------------------------------------------------------------------------
-  for (int pi = tid; pi < n_list * wmax; pi += kThreads) {
-    const int e = pi / wmax, k = pi - e * wmax;
-    const int c = cand[e];
-    const int l = c >> 24, m = c & 0xffffff;
-    const int s = ft.stride[l];
-    const int hwin = window_half(ft.radius[l], s);
-    if (k >= (2 * hwin + 1) * (2 * hwin + 1)) continue;
-    const int off = ft.point_off[l];
-    const int t0 = max(p_lo, off) - off;
-    const int t1 = min(p_hi, ft.point_off[l + 1]) - 1 - off;
-    // keys is indexed by the slice-local point index: (off + pos) - p_lo = pos - t0 + (off + t0 - p_lo)
-    window_vote(gts[m], k, hwin, s, ft.w[l], ft.h[l], t0, t1, ft.lo[l], ft.hi[l], ft.radius[l],
-                keys + (off + t0 - p_lo));
+  B200DET_STAMP_IF(traced, tslot + 1);
+  const int hwin = window_half(radius, s);
+  const int wcount = (2 * hwin + 1) * (2 * hwin + 1);
+  for (int pi = tid; pi < n_list * wcount; pi += kTrainThreads) {
+    const int e = pi / wcount, k = pi - e * wcount;
+    window_vote(gts[cand[e]], k, hwin, s, w, h, t0, t1, lo, hi, radius, keys);
   }
   __syncthreads();
+  B200DET_STAMP_IF(traced, tslot + 2);
 
-  // ---- 3. num_pos of the image ---------------------------------------------------------------------
+  // ---- pass A: the targets of every point, zero gradients of the negatives; at positives the
+  //      predictions are fetched (all of a thread's points in flight together) and the loss terms and
+  //      unscaled gradients evaluated — everything that does not need num_pos ------------------------------
+  const size_t out0 = (size_t)b * at.num_points + at.point_off[l];
+  const int p_first = t0 + tid;
+  unsigned pos_mask = 0;                                      // bit q: this thread's q-th point is positive
+  float4 pr[kTrainPts], tg[kTrainPts];
+  float px[kTrainPts], ct[kTrainPts];
   {
-    int c = 0;
-    for (int i = tid; i < n_own; i += kThreads) c += keys[i] != kNoWinner ? 1 : 0;
-    const int total = (int)block_sum_f((float)c, s_red);        // <= chunk < 2^24: exact in fp32
-    cluster.barrier_wait();
-    if (tid < csize) cluster.map_shared_rank(s_count, tid)[rank] = total;
-  }
-  cluster.sync();
-  int npos_i = 0;
-  for (int r = 0; r < csize; ++r) npos_i += s_count[r];
-  const float np = fmaxf((float)npos_i, 1.f);
-  const float scale_box = (grad_box ? grad_box[b] : inv_batch) / np;
-  const float scale_cnt = (grad_cnt ? grad_cnt[b] : inv_batch) / np;
-  const bool has_cnt = ft.has_cnt != 0;
-
-  // ---- 4a. targets of every point, zero gradients of the negatives ---------------------------------
-  const size_t out0 = (size_t)b * P;
-  for (int i = tid; i < n_own; i += kThreads) {
-    const int p = p_lo + i;
-    const int l = level_of(ft, p);
-    const int pos = p - ft.point_off[l];
-    const int hw = ft.hw[l];
-    const unsigned long long key = keys[i];
-    long long label = 0;
-    float cnt = -1.f;
-    float4 reg = make_float4(-1.f, -1.f, -1.f, -1.f);
-    const size_t base = (size_t)b * hw + pos;                  // index into a 1-channel map of the level
-    if (key != kNoWinner) {
-      const GtEntry g = gts[(unsigned)(key & 0xffffffffull)];
-      const int w = ft.w[l];
-      const int row = pos / w, col = pos - row * w;
-      positive_targets(g, col, row, ft.stride[l], &reg, &cnt);
-      label = (long long)g.label;
-      const float* rg = ft.reg[l] + (size_t)b * 4 * hw + pos;  // the predictions pass B will need
-      prefetch_l2(rg);
-      prefetch_l2(rg + hw);
-      prefetch_l2(rg + 2 * hw);
-      prefetch_l2(rg + 3 * hw);
-      if (has_cnt) prefetch_l2(ft.cnt[l] + base);
-    } else {
-      float* go = ft.greg[l] + (size_t)b * 4 * hw + pos;
-      stg_stream_f1(go, 0.f);
-      stg_stream_f1(go + hw, 0.f);
-      stg_stream_f1(go + 2 * hw, 0.f);
-      stg_stream_f1(go + 3 * hw, 0.f);
-      if (has_cnt) stg_stream_f1(ft.gcnt[l] + base, 0.f);
-    }
-    const size_t o = out0 + p;
-    stg_stream_s64(cls_t + o, label);
-    stg_stream_f1(cnt_t + o, cnt);
-    stg_stream_f4(reg_t + 4 * o, reg);
-  }
-
-  // ---- 4b. positives: loss terms and scaled gradients ----------------------------------------------
-  float acc_box = 0.f, acc_cnt = 0.f;
-  for (int i = tid; i < n_own; i += kThreads) {
-    const unsigned long long key = keys[i];
-    if (key == kNoWinner) continue;
-    const int p = p_lo + i;
-    const int l = level_of(ft, p);
-    const int pos = p - ft.point_off[l];
-    const int hw = ft.hw[l], w = ft.w[l];
-    const int row = pos / w, col = pos - row * w;
-    float4 tg;
-    float ct;
-    positive_targets(gts[(unsigned)(key & 0xffffffffull)], col, row, ft.stride[l], &tg, &ct);
-    const size_t rbase = (size_t)b * 4 * hw + pos;
-    const float* rg = ft.reg[l] + rbase;
-    const float4 pr = make_float4(rg[0], rg[hw], rg[2 * hw], rg[3 * hw]);
-    float4 g;
-    acc_box += box_term<true>(pr, tg, mode, &g);
-    float* go = ft.greg[l] + rbase;
-    stg_stream_f1(go, g.x * scale_box);
-    stg_stream_f1(go + hw, g.y * scale_box);
-    stg_stream_f1(go + 2 * hw, g.z * scale_box);
-    stg_stream_f1(go + 3 * hw, g.w * scale_box);
-    if (has_cnt) {
-      const size_t base = (size_t)b * hw + pos;
-      const float x = ft.cnt[l][base];
-      acc_cnt += bce_term(x, ct);
-      stg_stream_f1(ft.gcnt[l] + base, scale_cnt * (sigmoid_f32(x) - ct));
-    }
-  }
-
-  // ---- 5. per-image losses (rank order), batch means (image order) ---------------------------------
-  const float tot_box = block_sum_f(acc_box, s_red);
-  const float tot_cnt = block_sum_f(acc_cnt, s_red);
-  if (tid == 0) {
-    float* dst = cluster.map_shared_rank(s_part, 0);
-    dst[2 * rank] = tot_box;
-    dst[2 * rank + 1] = tot_cnt;
-  }
-  cluster.sync();
-  if (rank == 0 && tid == 0) {
-    float tb = 0.f, tc = 0.f;
-    for (int r = 0; r < csize; ++r) {
-      tb += s_part[2 * r];
-      tc += s_part[2 * r + 1];
-    }
-    box_loss[b] = tb / np;
-    if (cnt_loss) cnt_loss[b] = tc / np;
-    num_pos[b] = np;
-    if (mean_out) {
-      __threadfence();
-      const unsigned done = atomicAdd(ticket, 1u);
-      if (done == gridDim.y - 1) {                              // every other image's losses are visible
-        __threadfence();
-        float mb = 0.f, mc = 0.f;
-        for (unsigned i = 0; i < gridDim.y; ++i) {
-          mb += __ldcg(box_loss + i);
-          if (cnt_loss) mc += __ldcg(cnt_loss + i);
+    int row = p_first / w, col = p_first - row * w;
+    const int drow = kTrainThreads / w, dcol = kTrainThreads - drow * w;
+#pragma unroll
+    for (int q = 0; q < kTrainPts; ++q) {
+      const int pos = p_first + q * kTrainThreads;            // strided: every store instruction is coalesced
+      pr[q] = tg[q] = make_float4(-1.f, -1.f, -1.f, -1.f);
+      px[q] = 0.f;
+      ct[q] = -1.f;
+      if (pos < hw) {
+        const unsigned long long key = keys[pos - t0];
+        long long label = 0;
+        if (key != kNoWinner) {
+          const GtEntry g = gts[(unsigned)(key & 0xffffffffull)];
+          positive_targets(g, col, row, s, &tg[q], &ct[q]);
+          label = (long long)g.label;
+          pos_mask |= 1u << q;
+          pr[q] = make_float4(reg_p[pos], reg_p[hw + pos], reg_p[2 * hw + pos], reg_p[3 * hw + pos]);
+          if (has_cnt) px[q] = cnt_p[pos];
+        } else {
+          stg_stream_f1(greg + pos, 0.f);
+          stg_stream_f1(greg + hw + pos, 0.f);
+          stg_stream_f1(greg + 2 * hw + pos, 0.f);
+          stg_stream_f1(greg + 3 * hw + pos, 0.f);
+          if (has_cnt) stg_stream_f1(gcnt + pos, 0.f);
         }
-        mean_out[0] = mb / (float)gridDim.y;
-        mean_out[1] = mc / (float)gridDim.y;
-        *ticket = 0u;                                           // ready for the next launch
+        const size_t o = out0 + pos;
+        stg_stream_s64(cls_t + o, label);
+        stg_stream_f1(cnt_t + o, ct[q]);
+        stg_stream_f4(reg_t + 4 * o, tg[q]);
+      }
+      row += drow;
+      col += dcol;
+      if (col >= w) { col -= w; ++row; }
+    }
+  }
+  float acc_box = 0.f, acc_cnt = 0.f;
+  if (pos_mask) {
+#pragma unroll
+    for (int q = 0; q < kTrainPts; ++q) {
+      if (!(pos_mask & (1u << q))) continue;
+      float4 g;
+      acc_box += box_term<true>(pr[q], tg[q], mode, &g);
+      pr[q] = g;                                              // unscaled d(loss term) / d(l, t, r, b)
+      if (has_cnt) {
+        acc_cnt += bce_term(px[q], ct[q]);
+        px[q] = sigmoid_f32(px[q]) - ct[q];
       }
     }
+  }
+  B200DET_STAMP_IF(traced, tslot + 3);
+
+  // ---- pass B: scale the positives' gradients by grad_loss[b] / num_pos[b] and write them --------------
+  if (use_pdl) pdl_wait();                       // count_positives_kernel has completed and is visible
+  const int tile_has_pos = __syncthreads_or((int)pos_mask);
+  if (tile_has_pos) {
+    if (pos_mask) {
+      const float np = __ldcg(num_pos + b);
+      const float scale_box = (grad_box ? grad_box[b] : inv_batch) / np;
+      const float scale_cnt = (grad_cnt ? grad_cnt[b] : inv_batch) / np;
+#pragma unroll
+      for (int q = 0; q < kTrainPts; ++q) {
+        if (!(pos_mask & (1u << q))) continue;
+        const int pos = p_first + q * kTrainThreads;
+        stg_stream_f1(greg + pos, pr[q].x * scale_box);
+        stg_stream_f1(greg + hw + pos, pr[q].y * scale_box);
+        stg_stream_f1(greg + 2 * hw + pos, pr[q].z * scale_box);
+        stg_stream_f1(greg + 3 * hw + pos, pr[q].w * scale_box);
+        if (has_cnt) stg_stream_f1(gcnt + pos, scale_cnt * px[q]);
+      }
+    }
+    acc_box = block_sum_f(acc_box, s_red);
+    acc_cnt = block_sum_f(acc_cnt, s_red);
+  }
+  B200DET_STAMP_IF(traced, tslot + 4);
+
+  // ---- this tile's loss partials; finalize_losses_kernel adds them in tile order ------------------------
+  if (tid == 0) *reinterpret_cast<float2*>(partial + ((size_t)b * n_tiles + tile) * 2) = make_float2(acc_box, acc_cnt);
+  B200DET_STAMP_IF(traced, tslot + 5);
+}
+
+// ---- per-image losses (tile partials added in tile order), batch means (image order) ------------------
+// One CTA, launched as a programmatic dependent of the streaming kernel: it is resident before that kernel
+// ends and proceeds as soon as its partials are complete and visible.
+constexpr int kFinalThreads = 256;
+constexpr int kFinalStage = 2048;            // float2 partials staged per round
+
+__global__ void __launch_bounds__(kFinalThreads)
+finalize_losses_kernel(const int batch, const int n_tiles, const float* __restrict__ partial,
+                       const float* __restrict__ num_pos, float* __restrict__ box_loss, float* __restrict__ cnt_loss,
+                       float* __restrict__ mean_out, const int use_pdl) {
+  __shared__ float2 stage[kFinalStage];
+  __shared__ float2 img[kFinalStage];
+  if (use_pdl) pdl_wait();
+  const int tid = threadIdx.x;
+  const int per_round = kFinalStage / n_tiles;                 // images per round (n_tiles <= kFinalStage / 2)
+  float mb = 0.f, mc = 0.f;
+  for (int i0 = 0; i0 < batch; i0 += per_round) {
+    const int n = min(per_round, batch - i0);
+    __syncthreads();
+    const float2* src = reinterpret_cast<const float2*>(partial) + (size_t)i0 * n_tiles;
+    for (int t = tid; t < n * n_tiles; t += kFinalThreads) stage[t] = __ldcg(src + t);
+    __syncthreads();
+    for (int i = tid; i < n; i += kFinalThreads) {
+      float tb = 0.f, tc = 0.f;
+      for (int t = 0; t < n_tiles; ++t) {
+        tb += stage[i * n_tiles + t].x;
+        tc += stage[i * n_tiles + t].y;
+      }
+      const float np = __ldcg(num_pos + i0 + i);
+      tb /= np;
+      tc /= np;
+      box_loss[i0 + i] = tb;
+      if (cnt_loss) cnt_loss[i0 + i] = tc;
+      img[i] = make_float2(tb, tc);
+    }
+    __syncthreads();
+    if (tid == 0)
+      for (int i = 0; i < n; ++i) {
+        mb += img[i].x;
+        mc += img[i].y;
+      }
+  }
+  if (tid == 0 && mean_out) {
+    mean_out[0] = mb / (float)batch;
+    mean_out[1] = mc / (float)batch;
   }
 }
 
@@ -272,7 +349,16 @@ __global__ void __launch_bounds__(256) scale_maps_kernel(const ScaleTable t) {
 
 using namespace b200det;
 
-extern "C" size_t b200det_assign_loss_workspace_bytes(void) { return 256; }
+namespace {
+// workspace: [ticket] [tile partials B x tiles x 2]
+size_t ticket_bytes() { return 256; }
+int train_tiles(int num_points) { return (num_points + kTrainTile - 1) / kTrainTile + B200DET_MAX_LEVELS; }
+}  // namespace
+
+extern "C" size_t b200det_assign_loss_workspace_bytes(int batch, int num_points) {
+  if (batch <= 0 || num_points <= 0) return 0;
+  return ticket_bytes() + align_up((size_t)batch * train_tiles(num_points) * 2 * sizeof(float), 256);
+}
 
 extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* const* reg_grads, float* const* cnt_grads,
                                          int n_levels, const float* limit_lo, const float* limit_hi,
@@ -280,89 +366,80 @@ extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* con
                                          const int64_t* gt_labels, int mode, const float* grad_box,
                                          const float* grad_cnt, int64_t* cls_t, float* cnt_t, float* reg_t,
                                          float* box_loss, float* cnt_loss, float* num_pos, float* mean_out,
-                                         void* workspace, void* stream) {
+                                         void* workspace, size_t workspace_bytes, void* stream) {
   if (!levels || n_levels <= 0 || n_levels > B200DET_MAX_LEVELS || !limit_lo || !limit_hi || !radius_px ||
-      batch <= 0 || batch > 65535 || max_gt < 0 || max_gt >= (1 << 24) || !reg_grads || !cls_t || !cnt_t || !reg_t ||
-      !box_loss || !num_pos)
+      batch <= 0 || batch > 65535 || max_gt < 0 || !reg_grads || !cls_t || !cnt_t || !reg_t || !box_loss ||
+      !num_pos || !workspace)
     return B200DET_ERR_ARG;
   if (max_gt > 0 && (!gt_boxes || !gt_labels)) return B200DET_ERR_ARG;
-  if (!aligned16(gt_boxes) || !aligned16(reg_t)) return B200DET_ERR_ARG;
+  if (!aligned16(gt_boxes) || !aligned16(reg_t) || !aligned16(workspace)) return B200DET_ERR_ARG;
   if (mode != 0 && mode != 1) return B200DET_ERR_UNSUPPORTED;
-  if (mean_out && !workspace) return B200DET_ERR_ARG;
   const bool has_cnt = cnt_grads != nullptr;
   if (has_cnt != (cnt_loss != nullptr)) return B200DET_ERR_ARG;
-  FusedTable ft;
-  long long off = 0;
-  for (int l = 0; l < B200DET_MAX_LEVELS; ++l) {
-    const bool on = l < n_levels;
-    if (on) {
-      if (levels[l].h <= 0 || levels[l].w <= 0 || levels[l].stride <= 0 || !levels[l].reg || !reg_grads[l])
-        return B200DET_ERR_ARG;
-      if (has_cnt && (!levels[l].cnt || !cnt_grads[l])) return B200DET_ERR_ARG;
-    }
-    ft.reg[l] = on ? static_cast<const float*>(levels[l].reg) : nullptr;
-    ft.cnt[l] = on && has_cnt ? static_cast<const float*>(levels[l].cnt) : nullptr;
-    ft.greg[l] = on ? reg_grads[l] : nullptr;
-    ft.gcnt[l] = on && has_cnt ? cnt_grads[l] : nullptr;
-    ft.h[l] = on ? levels[l].h : 0;
-    ft.w[l] = on ? levels[l].w : 0;
-    ft.stride[l] = on ? levels[l].stride : 0;
-    ft.hw[l] = ft.h[l] * ft.w[l];
-    ft.lo[l] = on ? limit_lo[l] : 0.f;
-    ft.hi[l] = on ? limit_hi[l] : 0.f;
-    ft.radius[l] = on ? radius_px[l] : 0.f;
-    ft.point_off[l] = (int)off;
-    off += ft.hw[l];
-    if (off > (1ll << 30)) return B200DET_ERR_ARG;
+  int32_t level_hw[2 * B200DET_MAX_LEVELS], strides[B200DET_MAX_LEVELS];
+  LossMaps lm = {};
+  for (int l = 0; l < n_levels; ++l) {
+    if (!levels[l].reg || !reg_grads[l] || (has_cnt && (!levels[l].cnt || !cnt_grads[l]))) return B200DET_ERR_ARG;
+    level_hw[2 * l] = levels[l].h;
+    level_hw[2 * l + 1] = levels[l].w;
+    strides[l] = levels[l].stride;
+    lm.reg[l] = static_cast<const float*>(levels[l].reg);
+    lm.cnt[l] = has_cnt ? static_cast<const float*>(levels[l].cnt) : nullptr;
+    lm.greg[l] = reg_grads[l];
+    lm.gcnt[l] = has_cnt ? cnt_grads[l] : nullptr;
   }
-  ft.point_off[B200DET_MAX_LEVELS] = (int)off;
-  ft.n_levels = n_levels;
-  ft.num_points = (int)off;
-  ft.has_cnt = has_cnt ? 1 : 0;
+  const int tile_points = kTrainThreads * kTrainPts;
+  AssignTable at;
+  if (!make_assign_table(level_hw, strides, limit_lo, limit_hi, radius_px, n_levels, tile_points, &at))
+    return B200DET_ERR_ARG;
+  const int n_tiles = at.tile_off[B200DET_MAX_LEVELS];
+  if (n_tiles > 65535 || n_tiles > train_tiles(at.num_points)) return B200DET_ERR_UNSUPPORTED;
+  if (workspace_bytes < b200det_assign_loss_workspace_bytes(batch, at.num_points)) return B200DET_ERR_WORKSPACE;
+  if (n_tiles > kFinalStage / 2) return B200DET_ERR_UNSUPPORTED;       // finalize_losses_kernel stages whole images
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + ticket_bytes());
 
-  // Cluster size / CTA width.  B200DET_FUSED_CFG="<cluster>x<threads>" overrides (tuning knob).
-  int csize = 8, threads = 256;
-  static const char* cfg = getenv("B200DET_FUSED_CFG");
-  if (cfg) {
-    int c = 0, t = 0;
-    if (sscanf(cfg, "%dx%d", &c, &t) == 2 && (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) &&
-        (t == 128 || t == 256 || t == 512)) {
-      csize = c;
-      threads = t;
-    }
-  }
-  ft.chunk = (int)((off + csize - 1) / csize);
-  const size_t smem = (size_t)ft.chunk * 8 + (size_t)max_gt * (sizeof(GtEntry) + sizeof(int) * n_levels) + 16;
-  if (smem > 200 * 1024) return B200DET_ERR_UNSUPPORTED;
-
+  const size_t smem_count = (size_t)max_gt * sizeof(GtEntry) + (size_t)((at.num_points + 31) / 32) * 4;
+  const size_t smem_tile = (size_t)max_gt * (sizeof(GtEntry) + sizeof(int));
+  if (smem_count > 200 * 1024 || smem_tile > 180 * 1024) return B200DET_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  auto launch = [&](auto kernel) -> int {
-    cudaError_t e = cudaSuccess;
-    if (smem > 40 * 1024) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess && csize > 8) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
-    cudaLaunchConfig_t cfgl = {};
-    cfgl.gridDim = dim3(csize, batch);
-    cfgl.blockDim = dim3(threads);
-    cfgl.dynamicSmemBytes = smem;
-    cfgl.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = csize;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfgl.attrs = attr;
-    cfgl.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfgl, kernel, ft, max_gt, gt_boxes, reinterpret_cast<const long long*>(gt_labels), mode,
-                           grad_box, grad_cnt, 1.0f / (float)batch, reinterpret_cast<long long*>(cls_t), cnt_t, reg_t,
-                           box_loss, cnt_loss, num_pos, mean_out, static_cast<unsigned*>(workspace));
-    if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
-    return B200DET_OK;
-  };
-  const int rc = threads == 128 ? launch(assign_loss_fused_kernel<128>)
-               : threads == 512 ? launch(assign_loss_fused_kernel<512>)
-                                : launch(assign_loss_fused_kernel<256>);
+  cudaError_t e = cudaSuccess;
+  if (smem_count > 40 * 1024)
+    e = cudaFuncSetAttribute(count_positives_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count);
+  auto tile_kernel = assign_loss_tile_kernel;
+  if (e == cudaSuccess && smem_tile > 20 * 1024)
+    e = cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile);
+  if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
+
+  count_positives_kernel<<<dim3(kCountSlices, batch), kCountThreads, smem_count, st>>>(at, max_gt, gt_boxes, num_pos);
+  int rc = check_launch();
   if (rc) return rc;
+
+  // Programmatic dependent launch: the streaming kernel starts while count_positives_kernel runs and
+  // waits (griddepcontrol.wait) only before it reads num_pos.  B200DET_NO_PDL=1 serialises the two.
+  static const bool no_pdl = getenv("B200DET_NO_PDL") && getenv("B200DET_NO_PDL")[0] == '1';
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(batch, n_tiles);
+  cfg.blockDim = dim3(kTrainThreads);
+  cfg.dynamicSmemBytes = smem_tile;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  e = cudaLaunchKernelEx(&cfg, tile_kernel, at, lm, has_cnt ? 1 : 0, max_gt, gt_boxes,
+                         reinterpret_cast<const long long*>(gt_labels), mode, grad_box, grad_cnt,
+                         1.0f / (float)batch, (const float*)num_pos, reinterpret_cast<long long*>(cls_t), cnt_t, reg_t,
+                         partial, no_pdl ? 0 : 1);
+  if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
+  rc = check_launch();
+  if (rc) return rc;
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(kFinalThreads);
+  cfg.dynamicSmemBytes = 0;
+  e = cudaLaunchKernelEx(&cfg, finalize_losses_kernel, batch, n_tiles, (const float*)partial, (const float*)num_pos,
+                         box_loss, cnt_loss, mean_out, no_pdl ? 0 : 1);
+  if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
   return check_launch();
 }
 

@@ -23,7 +23,7 @@ launch_count = 0          # kernels launched through this module (bench.py repor
 # kernels per C entry point (see csrc/*.cu)
 _LAUNCHES = {"postprocess": 4, "batched_nms": 3, "score_points": 1, "select_topk": 1, "clip_boxes": 1,
              "assign_targets": 1, "box_loss_fwd": 1, "box_loss_bwd": 1, "cnt_loss_fwd": 1, "cnt_loss_bwd": 1,
-             "cls_loss_fwd": 2, "cls_loss_bwd": 1, "assign_loss_fused": 1, "scale_maps": 1}
+             "cls_loss_fwd": 2, "cls_loss_bwd": 1, "assign_loss_fused": 3, "scale_maps": 1}
 
 
 def _count(name: str) -> None:
@@ -404,18 +404,19 @@ def cls_loss_bwd(cls: Sequence[Tensor], cls_t: Tensor, grad_loss: Tensor, npos: 
 # --------------------------------------------------------------------------------------------
 # fused training step: targets + box / centerness loss forward and backward in one launch
 # --------------------------------------------------------------------------------------------
-_fused_ws = {}            # device index -> zeroed ticket buffer (the kernel leaves it zero)
+_fused_ws = {}            # (device index, batch, P) -> workspace (tile partials)
 
 
-def _fused_workspace(dev: torch.device) -> Tensor:
+def _fused_workspace(dev: torch.device, batch: int, p_total: int) -> Tensor:
     lib = _lib.load()
-    n = int(lib.b200det_assign_loss_workspace_bytes())
-    if torch.cuda.is_current_stream_capturing():
-        ws = _fused_ws.get(dev.index)
-        return ws if ws is not None else torch.zeros(n, dtype=torch.uint8, device=dev)
-    if dev.index not in _fused_ws:
-        _fused_ws[dev.index] = torch.zeros(n, dtype=torch.uint8, device=dev)
-    return _fused_ws[dev.index]
+    n = int(lib.b200det_assign_loss_workspace_bytes(batch, p_total))
+    key = (dev.index, batch, p_total)
+    ws = _fused_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(n, dtype=torch.uint8, device=dev)
+        if not torch.cuda.is_current_stream_capturing():     # a tensor of a graph's private pool is not cached
+            _fused_ws[key] = ws
+    return ws
 
 
 def assign_loss_fused(reg: Sequence[Tensor], cnt: Sequence[Tensor] | None, strides: Sequence[int],
@@ -428,7 +429,7 @@ def assign_loss_fused(reg: Sequence[Tensor], cnt: Sequence[Tensor] | None, strid
     box_loss / cnt_loss / num_pos [B], mean [2] (batch means of box_loss, cnt_loss), reg_grads /
     cnt_grads (lists shaped like the maps) = gradient of sum_b grad_*[b] * loss[b]; grad_* default to
     1/B, i.e. the gradient of the batch mean.  Concurrent calls on different streams of one device need
-    their own zero-initialised ``workspace`` (b200det_assign_loss_workspace_bytes() bytes).
+    their own ``workspace`` (b200det_assign_loss_workspace_bytes(B, P) bytes).
     """
     lib = _lib.load()
     lv, keep_alive, p_total, batch, n = _levels(None, cnt, reg, strides)
@@ -457,7 +458,7 @@ def assign_loss_fused(reg: Sequence[Tensor], cnt: Sequence[Tensor] | None, strid
     cnt_loss = torch.empty_like(box_loss) if cnt is not None else None
     num_pos = torch.empty_like(box_loss)
     mean = torch.empty((2,), dtype=torch.float32, device=dev) if want_mean else None
-    ws = workspace if workspace is not None else (_fused_workspace(dev) if want_mean else None)
+    ws = workspace if workspace is not None else _fused_workspace(dev, batch, p_total)
     gb = _f32c(grad_box, "grad_box").reshape(batch) if grad_box is not None else None
     gc = _f32c(grad_cnt, "grad_cnt").reshape(batch) if grad_cnt is not None else None
     ptr = lambda t: t.data_ptr() if t is not None else None
@@ -466,7 +467,7 @@ def assign_loss_fused(reg: Sequence[Tensor], cnt: Sequence[Tensor] | None, strid
                                            lo_arr, hi_arr, ra_arr, batch, m, gt.data_ptr(), lab.data_ptr(), int(mode),
                                            ptr(gb), ptr(gc), cls_t.data_ptr(), cnt_t.data_ptr(), reg_t.data_ptr(),
                                            box_loss.data_ptr(), ptr(cnt_loss), num_pos.data_ptr(), ptr(mean), ptr(ws),
-                                           _stream(gt))
+                                           ws.numel(), _stream(gt))
     _lib.check(rc, "b200det_assign_loss_fused")
     _count("assign_loss_fused")
     return {"cls_t": cls_t, "cnt_t": cnt_t, "reg_t": reg_t, "box_loss": box_loss, "cnt_loss": cnt_loss,
