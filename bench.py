@@ -377,9 +377,29 @@ def main():
         gen = B.FCOSGenTargets(W.STRIDES, W.HISFCOS_RANGES)
         fake = [torch.empty(TRAIN_BATCH, 1, h, w, device="meta") for h, w in W.COCO_LEVELS]
 
+        cnts = [[torch.randn(TRAIN_BATCH, 1, h, w, device=dev).requires_grad_(True) for h, w in W.COCO_LEVELS]
+                for _ in range(4)]
+        fused = B.FCOSTargetLoss(W.STRIDES, W.HISFCOS_RANGES, "giou")
+
         def train_step(i):
+            """Fused path: targets + GIoU loss + its gradients (3 PDL-chained launches) behind autograd."""
             for t in regs[i % 4]:
                 t.grad = None                              # optimizer.zero_grad(set_to_none=True)
+            loss, _ = fused.box_cnt_losses(None, regs[i % 4], gt, labels)
+            loss.backward()
+            return loss
+
+        def train_step_cnt(i):
+            """Same with the centerness BCE branch (loss.py:29-57) in the same launches."""
+            for t in regs[i % 4] + cnts[i % 4]:
+                t.grad = None
+            reg_loss, cnt_loss = fused.box_cnt_losses(cnts[i % 4], regs[i % 4], gt, labels)
+            (reg_loss + cnt_loss).backward()
+
+        def train_step_unfused(i):
+            """The drop-in modules one by one: FCOSGenTargets -> compute_reg_loss -> backward (3 kernels + glue)."""
+            for t in regs[i % 4]:
+                t.grad = None
             tgt = gen([[fake, fake, fake], gt, labels])
             loss = B.compute_reg_loss(regs[i % 4], tgt[2], None, "giou", _mask_src=tgt[1]).mean()
             loss.backward()
@@ -413,12 +433,22 @@ def main():
 
         with sampler:
             us = timed_graph(train_step, args.steps)
+            us_cnt = timed_graph(train_step_cnt, args.steps)
+            us_unfused = timed_graph(train_step_unfused, args.steps)
+            us_kernels = timed_graph(lambda i: ops.assign_loss_fused(regs[i % 4], None, W.STRIDES, W.HISFCOS_RANGES,
+                                                                    gt, labels, 1), args.steps)
             # assign alone, for its own roofline: 28 bytes written per point
             us_assign = timed_graph(
                 lambda i: ops.assign_targets(W.COCO_LEVELS, W.STRIDES, W.HISFCOS_RANGES, gt, labels), args.steps)
         assign_bytes = TRAIN_BATCH * P * 28 + TRAIN_BATCH * TRAIN_MAX_GT * 24
+        fused_bytes = TRAIN_BATCH * P * (28 + 16) + TRAIN_BATCH * TRAIN_MAX_GT * 24   # targets + reg gradients written
         train = {"workload": f"target assign + GIoU loss fwd+bwd, COCO 832x1344, B={TRAIN_BATCH}, M<={TRAIN_MAX_GT}",
-                 "us_per_batch": us, "assign_us": us_assign, "assign_bytes": assign_bytes,
+                 "us_per_batch": us, "path": "FCOSTargetLoss (fused: count + tile + finalize kernels, PDL-chained) + autograd",
+                 "fused_kernels_us": us_kernels, "fused_bytes": fused_bytes,
+                 "fused_gbs": fused_bytes / (us_kernels * 1e-6) / 1e9,
+                 "fused_frac_of_peak": fused_bytes / (us_kernels * 1e-6) / 1e9 / peak,
+                 "with_centerness_us": us_cnt, "unfused_us_per_batch": us_unfused,
+                 "assign_us": us_assign, "assign_bytes": assign_bytes,
                  "assign_gbs": assign_bytes / (us_assign * 1e-6) / 1e9,
                  "assign_frac_of_peak": assign_bytes / (us_assign * 1e-6) / 1e9 / peak}
 

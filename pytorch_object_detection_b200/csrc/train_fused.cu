@@ -249,32 +249,47 @@ assign_loss_tile_kernel(const AssignTable at, const LossMaps lm, const int has_c
   }
   B200DET_STAMP_IF(traced, tslot + 3);
 
+  // this tile's loss partials: fixed shuffle tree per warp, then the warps in order (one barrier)
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    acc_box += __shfl_xor_sync(0xffffffffu, acc_box, d);
+    acc_cnt += __shfl_xor_sync(0xffffffffu, acc_cnt, d);
+  }
+  if ((tid & 31) == 0) {
+    s_red[2 * (tid >> 5)] = acc_box;
+    s_red[2 * (tid >> 5) + 1] = acc_cnt;
+  }
+
   // ---- pass B: scale the positives' gradients by grad_loss[b] / num_pos[b] and write them --------------
   if (use_pdl) pdl_wait();                       // count_positives_kernel has completed and is visible
-  const int tile_has_pos = __syncthreads_or((int)pos_mask);
-  if (tile_has_pos) {
-    if (pos_mask) {
-      const float np = __ldcg(num_pos + b);
-      const float scale_box = (grad_box ? grad_box[b] : inv_batch) / np;
-      const float scale_cnt = (grad_cnt ? grad_cnt[b] : inv_batch) / np;
+  if (pos_mask) {
+    const float np = __ldcg(num_pos + b);
+    const float scale_box = (grad_box ? grad_box[b] : inv_batch) / np;
+    const float scale_cnt = (grad_cnt ? grad_cnt[b] : inv_batch) / np;
 #pragma unroll
-      for (int q = 0; q < kTrainPts; ++q) {
-        if (!(pos_mask & (1u << q))) continue;
-        const int pos = p_first + q * kTrainThreads;
-        stg_stream_f1(greg + pos, pr[q].x * scale_box);
-        stg_stream_f1(greg + hw + pos, pr[q].y * scale_box);
-        stg_stream_f1(greg + 2 * hw + pos, pr[q].z * scale_box);
-        stg_stream_f1(greg + 3 * hw + pos, pr[q].w * scale_box);
-        if (has_cnt) stg_stream_f1(gcnt + pos, scale_cnt * px[q]);
-      }
+    for (int q = 0; q < kTrainPts; ++q) {
+      if (!(pos_mask & (1u << q))) continue;
+      const int pos = p_first + q * kTrainThreads;
+      stg_stream_f1(greg + pos, pr[q].x * scale_box);
+      stg_stream_f1(greg + hw + pos, pr[q].y * scale_box);
+      stg_stream_f1(greg + 2 * hw + pos, pr[q].z * scale_box);
+      stg_stream_f1(greg + 3 * hw + pos, pr[q].w * scale_box);
+      if (has_cnt) stg_stream_f1(gcnt + pos, scale_cnt * px[q]);
     }
-    acc_box = block_sum_f(acc_box, s_red);
-    acc_cnt = block_sum_f(acc_cnt, s_red);
   }
   B200DET_STAMP_IF(traced, tslot + 4);
 
-  // ---- this tile's loss partials; finalize_losses_kernel adds them in tile order ------------------------
-  if (tid == 0) *reinterpret_cast<float2*>(partial + ((size_t)b * n_tiles + tile) * 2) = make_float2(acc_box, acc_cnt);
+  // finalize_losses_kernel adds the tile partials in tile order
+  __syncthreads();
+  if (tid == 0) {
+    float tb = 0.f, tc = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < kTrainThreads / 32; ++wi) {
+      tb += s_red[2 * wi];
+      tc += s_red[2 * wi + 1];
+    }
+    *reinterpret_cast<float2*>(partial + ((size_t)b * n_tiles + tile) * 2) = make_float2(tb, tc);
+  }
   B200DET_STAMP_IF(traced, tslot + 5);
 }
 
