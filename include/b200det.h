@@ -151,7 +151,7 @@ int b200det_cnt_loss_bwd(const b200det_level* levels, float* const* grads, int n
 
 /* Focal loss over ALL points (loss.py:6-26,180-193; alpha 0.25, gamma 2).  Reads levels[].cls.
  * workspace: b200det_cls_loss_workspace_bytes(). */
-size_t b200det_cls_loss_workspace_bytes(int batch, int num_points);
+size_t b200det_cls_loss_workspace_bytes(int batch, int num_points, int num_classes);
 int b200det_cls_loss_fwd(const b200det_level* levels, int n_levels, int batch, int num_classes,
                          const int64_t* cls_t, const float* cnt_t,
                          void* workspace, size_t workspace_bytes,

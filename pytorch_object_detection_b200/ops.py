@@ -375,7 +375,7 @@ def cls_loss_fwd(cls: Sequence[Tensor], mask_src: Tensor, cls_t: Tensor):
     _need_cuda(cls_t, "cls target")
     t = cls_t.to(torch.int64).reshape(batch, -1).contiguous()
     assert t.shape[1] == p_total
-    ws_bytes = lib.b200det_cls_loss_workspace_bytes(batch, p_total)
+    ws_bytes = lib.b200det_cls_loss_workspace_bytes(batch, p_total, keep_alive[0].shape[1])
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=m.device)
     loss = torch.empty((batch,), dtype=torch.float32, device=m.device)
     npos = torch.empty_like(loss)

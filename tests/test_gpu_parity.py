@@ -360,6 +360,26 @@ def test_known_answer_and_free_functions():
                  rel=REL_TOL)
 
 
+def test_focal_wide_logit_range():
+    """Focal loss and its gradient over logits in [-30, 14] (both branches of the in-kernel log, exp
+    overflow, the clip at 5e-6) against the reference formula evaluated by torch on the CPU (loss.py:180-193)."""
+    gen = torch.Generator().manual_seed(9)
+    n, c = 4096, 8
+    logits = torch.cat([torch.linspace(-30, 14, n * c // 2), (torch.rand(n * c // 2, generator=gen) - 0.5) * 16])
+    logits = logits[torch.randperm(n * c, generator=gen)].reshape(n, c)
+    hot = torch.zeros(n, c)
+    rows = torch.arange(0, n, 5)
+    hot[rows, rows % c] = 1
+    a = logits.clone().to(DEV).requires_grad_(True)
+    b = logits.clone().requires_grad_(True)
+    la = P.focal_loss_from_logits(a, hot.to(DEV))
+    lb = O.focal_sum(b, hot)
+    assert_close(float(la), float(lb), rel=REL_TOL)
+    la.backward()
+    lb.backward()
+    assert_close(to_np(a.grad), to_np(b.grad), rel=REL_TOL, abs_=1e-9)
+
+
 def test_box_loss_tie_subgradients_match_autograd():
     """Exact min/max ties (pred == target component) split the gradient 1/2-1/2 like torch."""
     p = torch.tensor([[4.0, 6.0, 8.0, 3.0], [2.0, 2.0, 2.0, 2.0], [1.0, 9.0, 4.0, 4.0]])

@@ -54,7 +54,7 @@ def test_workspace_sizes_are_host_only_and_monotone():
     assert lib.b200det_postprocess_workspace_bytes(16, 23265, _lib.MAX_BOX + 1) == 0
     assert lib.b200det_nms_workspace_bytes(1, 0) == 0
     assert lib.b200det_nms_workspace_bytes(4, 1000) > 4 * 1000 * 44
-    assert lib.b200det_cls_loss_workspace_bytes(32, 23265) >= 32 * 46 * 4
+    assert lib.b200det_cls_loss_workspace_bytes(32, 23265, 80) >= 32 * 46 * 5 * 4
 
 
 def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
