@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200DET_ABI_VERSION 3
+#define B200DET_ABI_VERSION 4
 #define B200DET_MAX_LEVELS 8
 #define B200DET_MAX_BOX 8192      /* largest max_detection_box / NMS candidate count per image */
 
@@ -37,7 +37,13 @@ typedef enum {
 } b200det_status;
 
 /* One FPN level of head outputs: cls [B,C,h,w], cnt [B,1,h,w], reg [B,4,h,w], fp32 (any may
- * be NULL where an entry point does not read it).  `stride` is the level's pixel stride; the
+ * be NULL where an entry point does not read it).  reg holds the (l, t, r, b) distances, or — when
+ * reg_scale is not NULL — the raw output x of the regression convolution, the distances being
+ * exp(x * *reg_scale): the reference's ScaleExp (model/modules/modules.py:170-176, applied at
+ * model/od/HISFcos.py:228) folded into the consumer, so the exp'd copy of reg is never written.
+ * reg_scale points to ONE fp32 on the device (the level's ScaleExp.scale parameter).  It is honoured by
+ * b200det_select_topk / b200det_postprocess and b200det_assign_loss_fused; the stand-alone box-loss
+ * entry points return B200DET_ERR_UNSUPPORTED for it.  `stride` is the level's pixel stride; the
  * point grid (j*stride + stride/2, i*stride + stride/2) of utill/utills.py:58-73 is computed
  * in-kernel, never materialised.  Points are numbered level-major, row-major inside a level
  * (the order reshape_cat_out produces, head.py:8-26); P = sum(h*w). */
@@ -46,6 +52,7 @@ typedef struct {
   const void* cnt;
   const void* reg;
   int32_t h, w, stride, pad_;
+  const void* reg_scale;
 } b200det_level;
 
 int         b200det_abi_version(void);
@@ -177,6 +184,8 @@ int b200det_cls_loss_bwd(const b200det_level* levels, float* const* grads, int n
  *   cls_t / cnt_t / reg_t : the targets, as b200det_assign_targets writes them (bit-identical)
  *   box_loss / cnt_loss / num_pos [B] f32 : as b200det_box_loss_fwd / b200det_cnt_loss_fwd
  *   mean_out [2] f32 or NULL : batch means of box_loss and cnt_loss, added in image order
+ *   reg_scale_grad [n_levels] f32 or NULL : d(sum_b grad_box[b] * box_loss[b]) / d(*levels[l].reg_scale)
+ *     (0 for levels without reg_scale); with reg_scale set, reg_grads are gradients w.r.t. the raw x
  *   workspace : b200det_assign_loss_workspace_bytes(batch, P) bytes (tile partials); one workspace per
  *     stream that may run this concurrently.
  * ------------------------------------------------------------------------------------- */
@@ -188,7 +197,7 @@ int b200det_assign_loss_fused(const b200det_level* levels, float* const* reg_gra
                               const float* grad_box, const float* grad_cnt,
                               int64_t* cls_t, float* cnt_t, float* reg_t,
                               float* box_loss, float* cnt_loss, float* num_pos, float* mean_out,
-                              void* workspace, size_t workspace_bytes, void* stream);
+                              float* reg_scale_grad, void* workspace, size_t workspace_bytes, void* stream);
 
 /* maps[i] (device, numel[i] floats) *= *factors[i] (device scalar) for i < n_maps <= 16; the arrays
  * themselves are HOST arrays.  A map whose factor is exactly 1 is not touched.  This is the autograd

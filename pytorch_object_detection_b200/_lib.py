@@ -14,13 +14,14 @@ from . import build as _build
 
 MAX_LEVELS = 8
 MAX_BOX = 8192
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class Level(C.Structure):
     """``b200det_level``."""
     _fields_ = [("cls", C.c_void_p), ("cnt", C.c_void_p), ("reg", C.c_void_p),
-                ("h", C.c_int32), ("w", C.c_int32), ("stride", C.c_int32), ("pad_", C.c_int32)]
+                ("h", C.c_int32), ("w", C.c_int32), ("stride", C.c_int32), ("pad_", C.c_int32),
+                ("reg_scale", C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -48,7 +49,7 @@ PROTOTYPES = {
     "b200det_cls_loss_bwd": (C.c_int, [_LV, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "b200det_assign_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "b200det_assign_loss_fused": (C.c_int, [_LV, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int,
-                                            _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+                                            _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "b200det_scale_maps": (C.c_int, [_P, _P, _P, C.c_int, _P]),
 }
 
@@ -95,10 +96,11 @@ def check(status: int, what: str) -> None:
 
 
 def make_levels(entries: Sequence[tuple]) -> C.Array:
-    """entries: (cls_ptr, cnt_ptr, reg_ptr, h, w, stride) per level; pointers may be 0/None."""
+    """entries: (cls_ptr, cnt_ptr, reg_ptr, h, w, stride[, reg_scale_ptr]) per level; pointers may be 0/None."""
     if not 0 < len(entries) <= MAX_LEVELS:
         raise B200DetError(f"between 1 and {MAX_LEVELS} levels are supported, got {len(entries)}")
     arr = (Level * len(entries))()
-    for i, (a, b, c, h, w, s) in enumerate(entries):
-        arr[i] = Level(a or None, b or None, c or None, h, w, s, 0)
+    for i, e in enumerate(entries):
+        a, b, c, h, w, s = e[:6]
+        arr[i] = Level(a or None, b or None, c or None, h, w, s, 0, (e[6] if len(e) > 6 else None) or None)
     return arr

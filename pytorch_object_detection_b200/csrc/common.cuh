@@ -23,6 +23,7 @@ struct LevelTable {
   const float* cls[B200DET_MAX_LEVELS];
   const float* cnt[B200DET_MAX_LEVELS];
   const float* reg[B200DET_MAX_LEVELS];
+  const float* reg_scale[B200DET_MAX_LEVELS];   // ScaleExp folded in: distances = exp(reg * *reg_scale); NULL = reg is final
   int h[B200DET_MAX_LEVELS];
   int w[B200DET_MAX_LEVELS];
   int stride[B200DET_MAX_LEVELS];
@@ -51,6 +52,7 @@ inline bool make_level_table(const b200det_level* levels, int n_levels, LevelTab
     t->cls[l] = static_cast<const float*>(levels[l].cls);
     t->cnt[l] = static_cast<const float*>(levels[l].cnt);
     t->reg[l] = static_cast<const float*>(levels[l].reg);
+    t->reg_scale[l] = static_cast<const float*>(levels[l].reg_scale);
     t->h[l] = levels[l].h;
     t->w[l] = levels[l].w;
     t->stride[l] = levels[l].stride;
@@ -68,7 +70,7 @@ inline bool make_level_table(const b200det_level* levels, int n_levels, LevelTab
     t->tile_off[l] = toff;
   }
   for (int l = n_levels; l < B200DET_MAX_LEVELS; ++l) {
-    t->cls[l] = t->cnt[l] = t->reg[l] = nullptr;
+    t->cls[l] = t->cnt[l] = t->reg[l] = t->reg_scale[l] = nullptr;
     t->h[l] = t->w[l] = t->stride[l] = t->hw[l] = t->vec_ok[l] = 0;
   }
   t->n_levels = n_levels;
@@ -120,6 +122,9 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // sigmoid as torch computes it: 1 / (1 + exp(-x)), IEEE division, full-precision expf.
 // (__frcp_rn is the correctly rounded reciprocal, i.e. bit-identical to 1.0f / y.)
 __device__ __forceinline__ float sigmoid_f32(float x) { return __frcp_rn(__fadd_rn(1.0f, expf(-x))); }
+
+// ScaleExp (modules.py:170-176): exp(x * scale), each op rounded as torch rounds it
+__device__ __forceinline__ float scale_exp_f32(float x, float scale) { return expf(__fmul_rn(x, scale)); }
 
 // streaming (read-once) loads that do not allocate in L1
 __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {

@@ -259,11 +259,16 @@ __device__ __forceinline__ SelectResult select_topk_cta(const LevelTable& lt, co
     const float x = (float)((pos % w) * s + s / 2);
     const float y = (float)((pos / w) * s + s / 2);
     const float* rg = lt.reg[l] + (size_t)b * 4 * hw + pos;
+    float4 d = make_float4(rg[0], rg[hw], rg[2 * hw], rg[3 * hw]);
+    if (lt.reg_scale[l]) {                                    // raw regression output: ScaleExp folded in
+      const float sc = *lt.reg_scale[l];
+      d = make_float4(scale_exp_f32(d.x, sc), scale_exp_f32(d.y, sc), scale_exp_f32(d.z, sc), scale_exp_f32(d.w, sc));
+    }
     float4 bx;
-    bx.x = __fsub_rn(x, rg[0]);
-    bx.y = __fsub_rn(y, rg[hw]);
-    bx.z = __fadd_rn(x, rg[2 * hw]);
-    bx.w = __fadd_rn(y, rg[3 * hw]);
+    bx.x = __fsub_rn(x, d.x);
+    bx.y = __fsub_rn(y, d.y);
+    bx.z = __fadd_rn(x, d.z);
+    bx.w = __fadd_rn(y, d.w);
     my_box = bx;
     my_cls = (int)cls0[(size_t)b * P + p] + 1;
     out.score[o0 + i] = key_to_float((uint32_t)(e >> 32));

@@ -43,6 +43,7 @@ namespace {
 
 struct LossMaps {
   const float* reg[B200DET_MAX_LEVELS];
+  const float* reg_scale[B200DET_MAX_LEVELS];   // ScaleExp folded in (common.cuh); NULL = reg holds the distances
   const float* cnt[B200DET_MAX_LEVELS];
   float* greg[B200DET_MAX_LEVELS];
   float* gcnt[B200DET_MAX_LEVELS];
@@ -130,6 +131,7 @@ constexpr int kTrainThreads = 256;
 constexpr int kTrainPts = 4;                  // 8 points per thread spills at the 64 registers 4 CTAs / SM allow
 constexpr int kTrainTile = kTrainThreads * kTrainPts;
 
+template <bool kScaleExp>                      // some level carries a folded ScaleExp (raw regression outputs)
 __global__ void __launch_bounds__(kTrainThreads, 3)
 assign_loss_tile_kernel(const AssignTable at, const LossMaps lm, const int has_cnt, const int M,
                         const float* __restrict__ gt_boxes, const long long* __restrict__ gt_labels, const int mode,
@@ -233,14 +235,27 @@ assign_loss_tile_kernel(const AssignTable at, const LossMaps lm, const int has_c
       if (col >= w) { col -= w; ++row; }
     }
   }
-  float acc_box = 0.f, acc_cnt = 0.f;
+  float acc_box = 0.f, acc_cnt = 0.f, acc_dsc = 0.f;
   if (pos_mask) {
+    const float sc = (kScaleExp && lm.reg_scale[l]) ? __ldg(lm.reg_scale[l]) : 0.f;
 #pragma unroll
     for (int q = 0; q < kTrainPts; ++q) {
       if (!(pos_mask & (1u << q))) continue;
       float4 g;
-      acc_box += box_term<true>(pr[q], tg[q], mode, &g);
-      pr[q] = g;                                              // unscaled d(loss term) / d(l, t, r, b)
+      if (kScaleExp && lm.reg_scale[l]) {
+        // raw regression output x: distances d = exp(x * sc) (ScaleExp); dL/dx = dL/dd * d * sc,
+        // dL/dsc += dL/dd * d * x
+        const float4 x4 = pr[q];
+        const float4 d4 = make_float4(scale_exp_f32(x4.x, sc), scale_exp_f32(x4.y, sc), scale_exp_f32(x4.z, sc),
+                                      scale_exp_f32(x4.w, sc));
+        acc_box += box_term<true>(d4, tg[q], mode, &g);
+        g = make_float4(g.x * d4.x, g.y * d4.y, g.z * d4.z, g.w * d4.w);
+        acc_dsc += (g.x * x4.x + g.y * x4.y) + (g.z * x4.z + g.w * x4.w);
+        g = make_float4(g.x * sc, g.y * sc, g.z * sc, g.w * sc);
+      } else {
+        acc_box += box_term<true>(pr[q], tg[q], mode, &g);
+      }
+      pr[q] = g;                                              // unscaled d(loss term) / d(reg map)
       if (has_cnt) {
         acc_cnt += bce_term(px[q], ct[q]);
         px[q] = sigmoid_f32(px[q]) - ct[q];
@@ -254,10 +269,12 @@ assign_loss_tile_kernel(const AssignTable at, const LossMaps lm, const int has_c
   for (int d = 16; d > 0; d >>= 1) {
     acc_box += __shfl_xor_sync(0xffffffffu, acc_box, d);
     acc_cnt += __shfl_xor_sync(0xffffffffu, acc_cnt, d);
+    acc_dsc += __shfl_xor_sync(0xffffffffu, acc_dsc, d);
   }
   if ((tid & 31) == 0) {
-    s_red[2 * (tid >> 5)] = acc_box;
-    s_red[2 * (tid >> 5) + 1] = acc_cnt;
+    s_red[3 * (tid >> 5)] = acc_box;
+    s_red[3 * (tid >> 5) + 1] = acc_cnt;
+    s_red[3 * (tid >> 5) + 2] = acc_dsc;
   }
 
   // ---- pass B: scale the positives' gradients by grad_loss[b] / num_pos[b] and write them --------------
@@ -282,13 +299,14 @@ assign_loss_tile_kernel(const AssignTable at, const LossMaps lm, const int has_c
   // finalize_losses_kernel adds the tile partials in tile order
   __syncthreads();
   if (tid == 0) {
-    float tb = 0.f, tc = 0.f;
+    float tb = 0.f, tc = 0.f, td = 0.f;
 #pragma unroll
     for (int wi = 0; wi < kTrainThreads / 32; ++wi) {
-      tb += s_red[2 * wi];
-      tc += s_red[2 * wi + 1];
+      tb += s_red[3 * wi];
+      tc += s_red[3 * wi + 1];
+      td += s_red[3 * wi + 2];
     }
-    *reinterpret_cast<float2*>(partial + ((size_t)b * n_tiles + tile) * 2) = make_float2(tb, tc);
+    *reinterpret_cast<float4*>(partial + ((size_t)b * n_tiles + tile) * 4) = make_float4(tb, tc, td, 0.f);
   }
   B200DET_STAMP_IF(traced, tslot + 5);
 }
@@ -297,31 +315,46 @@ assign_loss_tile_kernel(const AssignTable at, const LossMaps lm, const int has_c
 // One CTA, launched as a programmatic dependent of the streaming kernel: it is resident before that kernel
 // ends and proceeds as soon as its partials are complete and visible.
 constexpr int kFinalThreads = 256;
-constexpr int kFinalStage = 2048;            // float2 partials staged per round
+constexpr int kFinalStage = 1024;            // tile partials (float4: box, cnt, d/d scale, -) staged per round
+constexpr int kFinalImages = 128;            // images per round at most
+
+struct TileLevels {
+  int tile_off[B200DET_MAX_LEVELS + 1];
+  int n_levels;
+};
 
 __global__ void __launch_bounds__(kFinalThreads)
-finalize_losses_kernel(const int batch, const int n_tiles, const float* __restrict__ partial,
-                       const float* __restrict__ num_pos, float* __restrict__ box_loss, float* __restrict__ cnt_loss,
-                       float* __restrict__ mean_out, const int use_pdl) {
-  __shared__ float2 stage[kFinalStage];
-  __shared__ float2 img[kFinalStage];
+finalize_losses_kernel(const int batch, const int n_tiles, const TileLevels tl, const float* __restrict__ partial,
+                       const float* __restrict__ num_pos, const float* __restrict__ grad_box, const float inv_batch,
+                       float* __restrict__ box_loss, float* __restrict__ cnt_loss, float* __restrict__ mean_out,
+                       float* __restrict__ reg_scale_grad, const int use_pdl) {
+  __shared__ float4 stage[kFinalStage];
+  __shared__ float2 img[kFinalImages];
+  __shared__ float img_dsc[kFinalImages][B200DET_MAX_LEVELS];    // per image, per level: scaled d/d scale
   if (use_pdl) pdl_wait();
   const int tid = threadIdx.x;
-  const int per_round = kFinalStage / n_tiles;                 // images per round (n_tiles <= kFinalStage / 2)
-  float mb = 0.f, mc = 0.f;
+  const int per_round = min(kFinalImages, kFinalStage / n_tiles);   // images per round (n_tiles <= kFinalStage)
+  float mb = 0.f, mc = 0.f, my_dsc = 0.f;
   for (int i0 = 0; i0 < batch; i0 += per_round) {
     const int n = min(per_round, batch - i0);
     __syncthreads();
-    const float2* src = reinterpret_cast<const float2*>(partial) + (size_t)i0 * n_tiles;
+    const float4* src = reinterpret_cast<const float4*>(partial) + (size_t)i0 * n_tiles;
     for (int t = tid; t < n * n_tiles; t += kFinalThreads) stage[t] = __ldcg(src + t);
     __syncthreads();
     for (int i = tid; i < n; i += kFinalThreads) {
-      float tb = 0.f, tc = 0.f;
-      for (int t = 0; t < n_tiles; ++t) {
-        tb += stage[i * n_tiles + t].x;
-        tc += stage[i * n_tiles + t].y;
-      }
       const float np = __ldcg(num_pos + i0 + i);
+      const float up = (grad_box ? grad_box[i0 + i] : inv_batch) / np;
+      float tb = 0.f, tc = 0.f;
+      for (int l = 0; l < tl.n_levels; ++l) {
+        float td = 0.f;
+        for (int t = tl.tile_off[l]; t < tl.tile_off[l + 1]; ++t) {
+          const float4 v = stage[i * n_tiles + t];
+          tb += v.x;
+          tc += v.y;
+          td += v.z;
+        }
+        img_dsc[i][l] = td * up;
+      }
       tb /= np;
       tc /= np;
       box_loss[i0 + i] = tb;
@@ -334,11 +367,14 @@ finalize_losses_kernel(const int batch, const int n_tiles, const float* __restri
         mb += img[i].x;
         mc += img[i].y;
       }
+    if (tid < tl.n_levels)                                     // thread l: level l's scale gradient, image order
+      for (int i = 0; i < n; ++i) my_dsc += img_dsc[i][tid];
   }
   if (tid == 0 && mean_out) {
     mean_out[0] = mb / (float)batch;
     mean_out[1] = mc / (float)batch;
   }
+  if (reg_scale_grad && tid < tl.n_levels) reg_scale_grad[tid] = my_dsc;
 }
 
 // In-place multiply of up to kMaxScaleMaps arrays, each by its own device scalar; a map whose scalar is
@@ -372,7 +408,7 @@ int train_tiles(int num_points) { return (num_points + kTrainTile - 1) / kTrainT
 
 extern "C" size_t b200det_assign_loss_workspace_bytes(int batch, int num_points) {
   if (batch <= 0 || num_points <= 0) return 0;
-  return ticket_bytes() + align_up((size_t)batch * train_tiles(num_points) * 2 * sizeof(float), 256);
+  return ticket_bytes() + align_up((size_t)batch * train_tiles(num_points) * 4 * sizeof(float), 256);
 }
 
 extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* const* reg_grads, float* const* cnt_grads,
@@ -381,7 +417,8 @@ extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* con
                                          const int64_t* gt_labels, int mode, const float* grad_box,
                                          const float* grad_cnt, int64_t* cls_t, float* cnt_t, float* reg_t,
                                          float* box_loss, float* cnt_loss, float* num_pos, float* mean_out,
-                                         void* workspace, size_t workspace_bytes, void* stream) {
+                                         float* reg_scale_grad, void* workspace, size_t workspace_bytes,
+                                         void* stream) {
   if (!levels || n_levels <= 0 || n_levels > B200DET_MAX_LEVELS || !limit_lo || !limit_hi || !radius_px ||
       batch <= 0 || batch > 65535 || max_gt < 0 || !reg_grads || !cls_t || !cnt_t || !reg_t || !box_loss ||
       !num_pos || !workspace)
@@ -399,6 +436,7 @@ extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* con
     level_hw[2 * l + 1] = levels[l].w;
     strides[l] = levels[l].stride;
     lm.reg[l] = static_cast<const float*>(levels[l].reg);
+    lm.reg_scale[l] = static_cast<const float*>(levels[l].reg_scale);
     lm.cnt[l] = has_cnt ? static_cast<const float*>(levels[l].cnt) : nullptr;
     lm.greg[l] = reg_grads[l];
     lm.gcnt[l] = has_cnt ? cnt_grads[l] : nullptr;
@@ -410,7 +448,7 @@ extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* con
   const int n_tiles = at.tile_off[B200DET_MAX_LEVELS];
   if (n_tiles > 65535 || n_tiles > train_tiles(at.num_points)) return B200DET_ERR_UNSUPPORTED;
   if (workspace_bytes < b200det_assign_loss_workspace_bytes(batch, at.num_points)) return B200DET_ERR_WORKSPACE;
-  if (n_tiles > kFinalStage / 2) return B200DET_ERR_UNSUPPORTED;       // finalize_losses_kernel stages whole images
+  if (n_tiles > kFinalStage) return B200DET_ERR_UNSUPPORTED;           // finalize_losses_kernel stages whole images
   float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + ticket_bytes());
 
   const size_t smem_count = (size_t)max_gt * sizeof(GtEntry) + (size_t)((at.num_points + 31) / 32) * 4;
@@ -420,7 +458,9 @@ extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* con
   cudaError_t e = cudaSuccess;
   if (smem_count > 40 * 1024)
     e = cudaFuncSetAttribute(count_positives_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_count);
-  auto tile_kernel = assign_loss_tile_kernel;
+  bool scale_exp = false;
+  for (int l = 0; l < n_levels; ++l) scale_exp |= levels[l].reg_scale != nullptr;
+  auto tile_kernel = scale_exp ? assign_loss_tile_kernel<true> : assign_loss_tile_kernel<false>;
   if (e == cudaSuccess && smem_tile > 20 * 1024)
     e = cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile);
   if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
@@ -452,8 +492,12 @@ extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* con
   cfg.gridDim = dim3(1);
   cfg.blockDim = dim3(kFinalThreads);
   cfg.dynamicSmemBytes = 0;
-  e = cudaLaunchKernelEx(&cfg, finalize_losses_kernel, batch, n_tiles, (const float*)partial, (const float*)num_pos,
-                         box_loss, cnt_loss, mean_out, no_pdl ? 0 : 1);
+  TileLevels tl;
+  for (int l = 0; l <= B200DET_MAX_LEVELS; ++l) tl.tile_off[l] = at.tile_off[l];
+  tl.n_levels = n_levels;
+  e = cudaLaunchKernelEx(&cfg, finalize_losses_kernel, batch, n_tiles, tl, (const float*)partial,
+                         (const float*)num_pos, grad_box, 1.0f / (float)batch, box_loss, cnt_loss, mean_out,
+                         reg_scale_grad, no_pdl ? 0 : 1);
   if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
   return check_launch();
 }

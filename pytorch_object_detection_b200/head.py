@@ -28,12 +28,17 @@ def _ragged_error(counts: Sequence[int]) -> RuntimeError:
 class FCOSHead(nn.Module):
     """Inference post-processing: score, global top-k, threshold, batched NMS (head.py:41-102)."""
 
-    def __init__(self, score_threshold: float, nms_threshold: float, max_detection_box: int, strides: List[int]):
+    def __init__(self, score_threshold: float, nms_threshold: float, max_detection_box: int, strides: List[int],
+                 reg_exp_scales: Sequence[Tensor] | None = None):
+        """``reg_exp_scales`` (extension, default off): the head's per-level ``ScaleExp.scale`` parameters
+        (HISFcos.py:209,228).  When given, ``x[2]`` must hold the RAW ``reg_pred`` convolution outputs and the
+        ``exp(x * scale)`` pass of the model is evaluated inside the decode for the selected points only."""
         super().__init__()
         self.score = score_threshold
         self.nms_threshold = nms_threshold
         self.max_box = max_detection_box
         self.strides = strides
+        self.reg_exp_scales = reg_exp_scales
 
     # -- batched, padded contract (new: the reference cannot return ragged batches) ------------
     def detect(self, x, clip_hw: Tuple[int, int] | None = None, out_packed: Tensor | None = None):
@@ -41,9 +46,9 @@ class FCOSHead(nn.Module):
         boxes [B,K,4], counts [B] i32 (device tensors, no host sync); boxes are clipped to
         ``clip_hw`` = (H, W) when given (ClipBoxes fused into the writer).  ``out_packed`` places
         the outputs in a caller-owned buffer (see ``ops.postprocess``)."""
-        if out_packed is not None:
+        if out_packed is not None or self.reg_exp_scales is not None:
             s, c, b, _, n = ops.postprocess(x[0], x[1], x[2], self.strides, self.score, self.nms_threshold,
-                                            self.max_box, clip_hw, out_packed)
+                                            self.max_box, clip_hw, out_packed, self.reg_exp_scales)
             return s, c, b, n
         s, c, b, _, n = torch.ops.b200det.postprocess(
             list(x[0]), list(x[1]), list(x[2]), [int(v) for v in self.strides], float(self.score),

@@ -159,12 +159,15 @@ class _FusedTargetLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, gt_boxes: Tensor, labels: Tensor, cfg, *maps: Tensor):
-        strides, limit_range, mode, radius, n_reg = cfg
-        reg, cnt = maps[:n_reg], (maps[n_reg:] or None)
-        r = ops.assign_loss_fused(reg, cnt, strides, limit_range, gt_boxes, labels, mode, radius)
+        strides, limit_range, mode, radius, n_reg, n_cnt = cfg
+        reg, cnt, scales = maps[:n_reg], (maps[n_reg:n_reg + n_cnt] or None), (maps[n_reg + n_cnt:] or None)
+        r = ops.assign_loss_fused(reg, cnt, strides, limit_range, gt_boxes, labels, mode, radius,
+                                  reg_exp_scales=scales)
         ctx.n_reg, ctx.has_cnt = n_reg, cnt is not None
         ctx.dtypes = [t.dtype for t in maps]
-        ctx.save_for_backward(*r["reg_grads"], *(r["cnt_grads"] or []))
+        ctx.scale_shapes = [t.shape for t in scales] if scales else []
+        ctx.save_for_backward(*r["reg_grads"], *(r["cnt_grads"] or []),
+                              *([r["scale_grad"]] if scales else []))
         ctx.set_materialize_grads(False)
         mean = r["mean"]
         aux = [r["cls_t"], r["cnt_t"], r["reg_t"], r["box_loss"], r["num_pos"]] + ([r["cnt_loss"]] if cnt else [])
@@ -178,6 +181,7 @@ class _FusedTargetLoss(torch.autograd.Function):
         ctx.consumed = True
         grads = list(ctx.saved_tensors)
         n = ctx.n_reg
+        scale_grad = grads.pop() if ctx.scale_shapes else None
         todo, factors = [], []
         for i, g in enumerate(grads):
             up = g_box if i < n else g_cnt
@@ -186,9 +190,14 @@ class _FusedTargetLoss(torch.autograd.Function):
             else:
                 todo.append(g)
                 factors.append(up.detach().to(torch.float32).reshape(()))
+        if scale_grad is not None and g_box is not None:
+            todo.append(scale_grad)
+            factors.append(g_box.detach().to(torch.float32).reshape(()))
         if todo:
             ops.scale_maps_(todo, factors)
         out = [g if g is None else g.to(dt) for g, dt in zip(grads, ctx.dtypes)]
+        if scale_grad is not None:                  # one gradient per ScaleExp.scale parameter
+            out += [None if g_box is None else scale_grad[i].reshape(shp) for i, shp in enumerate(ctx.scale_shapes)]
         return (None, None, None, *out)
 
 
@@ -203,7 +212,10 @@ class FCOSTargetLoss(nn.Module):
     """
 
     def __init__(self, strides: Sequence[int], limit_range: Sequence[Sequence[float]], mode: str = "giou",
-                 sample_radio_ratio: float = 1.5):
+                 sample_radio_ratio: float = 1.5, reg_exp_scales: Sequence[Tensor] | None = None):
+        """``reg_exp_scales`` (extension, default off): the head's per-level ``ScaleExp.scale`` parameters
+        (HISFcos.py:209,228).  When given, ``reg_preds`` must be the RAW ``reg_pred`` convolution outputs:
+        ``exp(x * scale)`` is evaluated at the positives inside the kernel, gradients flow to x and to the scales."""
         super().__init__()
         assert len(strides) == len(limit_range)                          # head.py:216
         if mode not in _MODES:
@@ -212,13 +224,17 @@ class FCOSTargetLoss(nn.Module):
         self.limit_range = [tuple(float(v) for v in r) for r in limit_range]
         self.mode = mode
         self.sample_radio_ratio = float(sample_radio_ratio)
+        self.reg_exp_scales = reg_exp_scales
         self.targets = None
 
     def box_cnt_losses(self, cnt_logits, reg_preds, gt_boxes: Tensor, labels: Tensor):
         """(reg_loss, cnt_loss) batch means + targets; ``cnt_logits`` may be None (box loss only)."""
         n = min(len(self.strides), len(reg_preds), len(cnt_logits) if cnt_logits is not None else len(reg_preds))
-        cfg = (self.strides[:n], self.limit_range[:n], _MODES[self.mode], self.sample_radio_ratio, n)
+        n_cnt = n if cnt_logits is not None else 0
+        cfg = (self.strides[:n], self.limit_range[:n], _MODES[self.mode], self.sample_radio_ratio, n, n_cnt)
         maps = list(reg_preds[:n]) + (list(cnt_logits[:n]) if cnt_logits is not None else [])
+        if self.reg_exp_scales is not None:
+            maps += list(self.reg_exp_scales)[:n]
         out = _FusedTargetLoss.apply(gt_boxes, labels, cfg, *maps)
         self.targets = (out[2], out[3], out[4])
         self.per_image = {"reg": out[5], "num_pos": out[6], "cnt": out[7] if cnt_logits is not None else None}

@@ -48,8 +48,26 @@ def _f32c(t: Tensor, what: str) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _scale_ptrs(reg_exp_scales, n: int, keep: List[Tensor]):
+    """Device pointers of the per-level ScaleExp.scale parameters (modules.py:170-176), or Nones."""
+    if reg_exp_scales is None:
+        return [None] * n
+    if len(reg_exp_scales) < n:
+        raise _lib.B200DetError("reg_exp_scales is shorter than the level list")
+    out = []
+    for t in list(reg_exp_scales)[:n]:
+        _need_cuda(t, "reg_exp_scale")
+        t = t.detach()
+        if t.dtype != torch.float32 or t.numel() != 1:
+            raise _lib.B200DetError("a reg_exp_scale must be ONE fp32 value (ScaleExp.scale)")
+        t = t.contiguous()
+        keep.append(t)
+        out.append(t.data_ptr())
+    return out
+
+
 def _levels(cls: Sequence[Tensor] | None, cnt: Sequence[Tensor] | None, reg: Sequence[Tensor] | None,
-            strides: Sequence[int]):
+            strides: Sequence[int], reg_exp_scales=None):
     """zip()-truncated level table.  Returns (ctypes array, kept tensors, P, batch, n_levels)."""
     lists = [l for l in (cls, cnt, reg) if l is not None]
     n = min([len(strides)] + [len(l) for l in lists])
@@ -81,6 +99,12 @@ def _levels(cls: Sequence[Tensor] | None, cnt: Sequence[Tensor] | None, reg: Seq
             ptrs.append(t.data_ptr())
         entries.append((ptrs[0], ptrs[1], ptrs[2], hw[0], hw[1], int(strides[i])))
         p_total += hw[0] * hw[1]
+    if reg_exp_scales is not None:
+        n_maps = len(keep)
+        scales = _scale_ptrs(reg_exp_scales, n, keep)
+        entries = [e + (sp,) for e, sp in zip(entries, scales)]
+        keep_maps, keep_scales = keep[:n_maps], keep[n_maps:]
+        keep = keep_maps + keep_scales          # maps first: callers slice keep[:...] by map count
     return _lib.make_levels(entries), keep, p_total, batch, n
 
 
@@ -89,8 +113,12 @@ def _levels(cls: Sequence[Tensor] | None, cnt: Sequence[Tensor] | None, reg: Seq
 # --------------------------------------------------------------------------------------------
 def postprocess(cls: Sequence[Tensor], cnt: Sequence[Tensor], reg: Sequence[Tensor], strides: Sequence[int],
                 score_thr: float, nms_thr: float, max_box: int, clip_hw: Tuple[int, int] | None = None,
-                out_packed: Tensor | None = None):
+                out_packed: Tensor | None = None, reg_exp_scales: Sequence[Tensor] | None = None):
     """FCOSHead.forward (+ ClipBoxes) for any batch size, padded outputs.
+
+    With ``reg_exp_scales`` (one 1-element CUDA tensor per level: the head's ``ScaleExp.scale``), ``reg`` holds
+    the RAW regression convolution outputs and ``exp(reg * scale)`` (HISFcos.py:228) is evaluated inside the
+    decode, only for the <= max_box selected points.
 
     Returns scores [B,K] f32, classes [B,K] i64 (1-based), boxes [B,K,4] f32, keep [B,K] i64,
     counts [B] i32 with K = min(max_box, P); rows beyond counts[b] are unspecified.  All five share
@@ -98,7 +126,7 @@ def postprocess(cls: Sequence[Tensor], cnt: Sequence[Tensor], reg: Sequence[Tens
     caller place it, e.g. inside a buffer that one collective gathers for several batches.
     """
     lib = _lib.load()
-    lv, keep_alive, p_total, batch, n = _levels(cls, cnt, reg, strides)
+    lv, keep_alive, p_total, batch, n = _levels(cls, cnt, reg, strides, reg_exp_scales)
     dev = keep_alive[0].device
     k = min(int(max_box), p_total)
     if k > _lib.MAX_BOX:
@@ -422,17 +450,20 @@ def _fused_workspace(dev: torch.device, batch: int, p_total: int) -> Tensor:
 def assign_loss_fused(reg: Sequence[Tensor], cnt: Sequence[Tensor] | None, strides: Sequence[int],
                       limit_range: Sequence[Sequence[float]], gt_boxes: Tensor, labels: Tensor, mode: int,
                       sample_radius: float = 1.5, grad_box: Tensor | None = None, grad_cnt: Tensor | None = None,
-                      want_mean: bool = True, workspace: Tensor | None = None):
+                      want_mean: bool = True, workspace: Tensor | None = None,
+                      reg_exp_scales: Sequence[Tensor] | None = None):
     """FCOSGenTargets.forward + compute_reg_loss (+ compute_cnt_loss) forward AND backward, one kernel.
 
     Returns a dict: cls_t [B,P,1] i64, cnt_t [B,P,1], reg_t [B,P,4] (bit-identical to assign_targets),
     box_loss / cnt_loss / num_pos [B], mean [2] (batch means of box_loss, cnt_loss), reg_grads /
     cnt_grads (lists shaped like the maps) = gradient of sum_b grad_*[b] * loss[b]; grad_* default to
-    1/B, i.e. the gradient of the batch mean.  Concurrent calls on different streams of one device need
+    1/B, i.e. the gradient of the batch mean.  With ``reg_exp_scales`` (per level ONE fp32 CUDA value, the
+    head's ScaleExp.scale) ``reg`` holds the raw regression outputs x, the distances are exp(x * scale),
+    reg_grads are gradients w.r.t. x and ``scale_grad`` [n_levels] w.r.t. the scales.  Concurrent calls on different streams of one device need
     their own ``workspace`` (b200det_assign_loss_workspace_bytes(B, P) bytes).
     """
     lib = _lib.load()
-    lv, keep_alive, p_total, batch, n = _levels(None, cnt, reg, strides)
+    lv, keep_alive, p_total, batch, n = _levels(None, cnt, reg, strides, reg_exp_scales)
     if len(limit_range) < n:
         raise _lib.B200DetError("limit_range is shorter than the level list")
     _need_cuda(gt_boxes, "gt_boxes")
@@ -447,8 +478,9 @@ def assign_loss_fused(reg: Sequence[Tensor], cnt: Sequence[Tensor] | None, strid
     hi_arr = (C.c_float * n)(*[float(r[1]) for r in limit_range[:n]])
     ra_arr = (C.c_float * n)(*[float(s * sample_radius) for s in list(strides)[:n]])
     per = 2 if cnt is not None else 1
-    maps_cnt = keep_alive[0::per][:n] if cnt is not None else None      # _levels appends (cnt, reg) per level
-    maps_reg = keep_alive[1::per][:n] if cnt is not None else keep_alive[:n]
+    maps = keep_alive[:per * n]                                         # (scale tensors follow the maps)
+    maps_cnt = maps[0::per] if cnt is not None else None                # _levels appends (cnt, reg) per level
+    maps_reg = maps[1::per] if cnt is not None else maps
     reg_grads = [torch.empty_like(x) for x in maps_reg]
     cnt_grads = [torch.empty_like(x) for x in maps_cnt] if cnt is not None else None
     cls_t = torch.empty((batch, p_total, 1), dtype=torch.int64, device=dev)
@@ -458,6 +490,7 @@ def assign_loss_fused(reg: Sequence[Tensor], cnt: Sequence[Tensor] | None, strid
     cnt_loss = torch.empty_like(box_loss) if cnt is not None else None
     num_pos = torch.empty_like(box_loss)
     mean = torch.empty((2,), dtype=torch.float32, device=dev) if want_mean else None
+    scale_grad = torch.empty((n,), dtype=torch.float32, device=dev) if reg_exp_scales is not None else None
     ws = workspace if workspace is not None else _fused_workspace(dev, batch, p_total)
     gb = _f32c(grad_box, "grad_box").reshape(batch) if grad_box is not None else None
     gc = _f32c(grad_cnt, "grad_cnt").reshape(batch) if grad_cnt is not None else None
@@ -466,12 +499,13 @@ def assign_loss_fused(reg: Sequence[Tensor], cnt: Sequence[Tensor] | None, strid
         rc = lib.b200det_assign_loss_fused(lv, _grad_ptrs(reg_grads), _grad_ptrs(cnt_grads) if cnt_grads else None, n,
                                            lo_arr, hi_arr, ra_arr, batch, m, gt.data_ptr(), lab.data_ptr(), int(mode),
                                            ptr(gb), ptr(gc), cls_t.data_ptr(), cnt_t.data_ptr(), reg_t.data_ptr(),
-                                           box_loss.data_ptr(), ptr(cnt_loss), num_pos.data_ptr(), ptr(mean), ptr(ws),
-                                           ws.numel(), _stream(gt))
+                                           box_loss.data_ptr(), ptr(cnt_loss), num_pos.data_ptr(), ptr(mean),
+                                           ptr(scale_grad), ptr(ws), ws.numel(), _stream(gt))
     _lib.check(rc, "b200det_assign_loss_fused")
     _count("assign_loss_fused")
     return {"cls_t": cls_t, "cnt_t": cnt_t, "reg_t": reg_t, "box_loss": box_loss, "cnt_loss": cnt_loss,
-            "num_pos": num_pos, "mean": mean, "reg_grads": reg_grads, "cnt_grads": cnt_grads}
+            "num_pos": num_pos, "mean": mean, "reg_grads": reg_grads, "cnt_grads": cnt_grads,
+            "scale_grad": scale_grad}
 
 
 def scale_maps_(maps: Sequence[Tensor], factors: Sequence[Tensor]) -> None:

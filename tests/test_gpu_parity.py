@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 if torch.cuda.is_available():
     import pytorch_object_detection_b200 as P
-    from pytorch_object_detection_b200 import ops
+    from pytorch_object_detection_b200 import _lib, ops
 DEV = "cuda:0"
 
 
@@ -498,6 +498,67 @@ def test_fused_target_loss_edge_cases():
     # dense crowd: BASELINE config 4's assignment side
     gt, labels = W.gt_boxes(4, 300, W.COCO_HW, 80, seed=78)
     check(W.COCO_LEVELS, gt, labels, W.HISFCOS_RANGES)
+
+
+# ------------------------------------------------------------------------------------------
+# N2: ScaleExp (exp(x * scale), modules.py:170-176 / HISFcos.py:228) folded into the consumers
+# ------------------------------------------------------------------------------------------
+def _raw_reg_case(batch, levels, ncls, seed):
+    """Head outputs whose regression branch is still RAW (before ScaleExp) plus per-level scales."""
+    gen = torch.Generator().manual_seed(seed)
+    x = W.head_outputs(batch, ncls, levels, seed)
+    scales = [torch.tensor([1.2 - 0.07 * i]) for i in range(len(levels))]               # HISFcos.py:209: init 1.2
+    raw = [torch.randn(batch, 4, h, w, generator=gen) * 0.6 + 2.2 for h, w in levels]   # exp(1.2 * 2.2) ~ 14 px
+    return x, raw, scales
+
+
+def test_head_with_folded_scale_exp_matches_reference_order():
+    """FCOSHead(reg_exp_scales=...) on raw reg outputs == the reference head on exp(raw * scale)."""
+    x, raw, scales = _raw_reg_case(2, W.COCO_LEVELS, 80, seed=91)
+    reg_ref = [torch.exp(r * s) for r, s in zip(raw, scales)]                # what HISFCOSHead.forward emits
+    want = O.detect((x[0], x[1], reg_ref), 0.05, 0.6, 1000, W.STRIDES)
+    head = P.FCOSHead(0.05, 0.6, 1000, W.STRIDES, reg_exp_scales=[s.to(DEV) for s in scales])
+    s_, c_, b_, n_ = head.detect(([t.to(DEV) for t in x[0]], [t.to(DEV) for t in x[1]], [r.to(DEV) for r in raw]))
+    for i, (ws, wc, wb) in enumerate(want):
+        k = int(n_[i])
+        assert_detections_match((to_np(s_[i, :k]), to_np(c_[i, :k]), to_np(b_[i, :k])),
+                                (to_np(ws), to_np(wc), to_np(wb)), what=f"image {i}")
+
+
+@pytest.mark.parametrize("mode", ["giou", "iou"])
+def test_fused_target_loss_with_folded_scale_exp(mode):
+    """Gradients w.r.t. the raw regression outputs AND the ScaleExp scales against CPU autograd through
+    exp(raw * scale) -> reference assignment -> reference losses."""
+    B, M = 3, 12
+    x, raw, scales = _raw_reg_case(B, W.COCO_LEVELS, 80, seed=92)
+    gt, labels = W.gt_boxes(B, M, W.COCO_HW, 80, seed=93)
+    # CPU reference
+    raw_c = [r.clone().requires_grad_(True) for r in raw]
+    sc_c = [s.clone().requires_grad_(True) for s in scales]
+    cnt_c = [t.clone().requires_grad_(True) for t in x[1]]
+    reg_c = [torch.exp(r * s) for r, s in zip(raw_c, sc_c)]
+    tgt = O.assign_targets(W.COCO_LEVELS, gt, labels, W.STRIDES, W.HISFCOS_RANGES)
+    mask = tgt[1].squeeze(-1) > -1
+    want_reg = O.reg_loss(reg_c, tgt[2], mask, mode).mean()
+    want_cnt = O.cnt_loss(cnt_c, tgt[1], mask).mean()
+    (want_reg + 0.5 * want_cnt).backward()
+    # fused CUDA path
+    raw_g = [r.clone().to(DEV).requires_grad_(True) for r in raw]
+    sc_g = [s.clone().to(DEV).requires_grad_(True) for s in scales]
+    cnt_g = [t.clone().to(DEV).requires_grad_(True) for t in x[1]]
+    step = P.FCOSTargetLoss(W.STRIDES, W.HISFCOS_RANGES, mode, reg_exp_scales=sc_g)
+    got_reg, got_cnt = step.box_cnt_losses(cnt_g, raw_g, gt.to(DEV), labels.to(DEV))
+    assert_close(float(got_reg), float(want_reg), rel=REL_TOL)
+    assert_close(float(got_cnt), float(want_cnt), rel=REL_TOL)
+    (got_reg + 0.5 * got_cnt).backward()
+    for a, w in zip(raw_g + cnt_g, raw_c + cnt_c):
+        assert_close(to_np(a.grad), to_np(w.grad), rel=REL_TOL, abs_=1e-9)
+    for lv, (a, w) in enumerate(zip(sc_g, sc_c)):
+        assert a.grad.shape == w.grad.shape
+        assert_close(to_np(a.grad), to_np(w.grad), rel=2e-5, abs_=1e-7, what=f"scale grad level {lv}")
+    # the stand-alone box-loss entry points refuse the folded form instead of mis-reading raw values
+    lv, keep, *_ = ops._levels(None, None, raw_g, [1] * 5, sc_g)
+    assert _lib.load().b200det_box_loss_fwd(lv, 5, B, 0, 0, 1, 0, 0, None) != 0
 
 
 # ------------------------------------------------------------------------------------------
