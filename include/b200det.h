@@ -205,6 +205,23 @@ int b200det_assign_loss_fused(const b200det_level* levels, float* const* reg_gra
 int b200det_scale_maps(float* const* maps, const int64_t* numel, const float* const* factors, int n_maps,
                        void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * N4 — the datasets' collate_fn on the device (dataset/voc.py:141-173, dataset/coco.py:135-165).
+ * ------------------------------------------------------------------------------------- */
+
+/* Ragged GT lists -> padded batch.  flat_boxes [N,4] f32 and flat_labels [N] i64 hold the images' rows back
+ * to back, offsets [batch+1] i32 (device) the row range of each image.  Writes gt_boxes [batch,max_gt,4]
+ * and gt_labels [batch,max_gt], rows beyond an image's count = -1 (F.pad(..., value=-1) + torch.stack). */
+int b200det_pack_gt(const float* flat_boxes, const int64_t* flat_labels, const int32_t* offsets,
+                    int batch, int max_gt, float* gt_boxes, int64_t* gt_labels, void* stream);
+
+/* images[b] (HOST array of device pointers) = image b, [channels,h_b,w_b] f32 with image_hw[2b] = h_b,
+ * image_hw[2b+1] = w_b (host).  out [batch,channels,out_h,out_w] = Normalize(mean, std)(zero-pad(image)):
+ * a padded pixel is (0 - mean[c]) / std[c], as in the reference, which normalises AFTER padding.
+ * mean / std are host arrays of `channels` floats. */
+int b200det_collate_images(const void* const* images, const int32_t* image_hw, int batch, int channels,
+                           int out_h, int out_w, const float* mean, const float* std, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,8 @@ PROTOTYPES = {
     "b200det_assign_loss_fused": (C.c_int, [_LV, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int,
                                             _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "b200det_scale_maps": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "b200det_pack_gt": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "b200det_collate_images": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -562,6 +562,53 @@ def test_fused_target_loss_with_folded_scale_exp(mode):
 
 
 # ------------------------------------------------------------------------------------------
+# N4: the datasets' collate_fn on the device
+# ------------------------------------------------------------------------------------------
+def _reference_collate(data, mean, std):
+    """dataset/voc.py:141-173 restated with torch CPU ops (Normalize = (x - mean) / std after the zero pad)."""
+    imgs, boxes, classes = zip(*data)
+    max_h, max_w = max(t.shape[1] for t in imgs), max(t.shape[2] for t in imgs)
+    m = torch.tensor(mean).view(-1, 1, 1)
+    s = torch.tensor(std).view(-1, 1, 1)
+    out_imgs = torch.stack([(torch.nn.functional.pad(t, (0, max_w - t.shape[2], 0, max_h - t.shape[1]), value=0.) - m) / s
+                            for t in imgs])
+    max_num = max(b.shape[0] for b in boxes)
+    out_boxes = torch.stack([torch.nn.functional.pad(b, (0, 0, 0, max_num - b.shape[0]), value=-1) for b in boxes])
+    out_cls = torch.stack([torch.nn.functional.pad(c, (0, max_num - c.shape[0]), value=-1) for c in classes])
+    return out_imgs, out_boxes, out_cls
+
+
+@pytest.mark.parametrize("sizes", [[(37, 53), (64, 41), (5, 64)], [(32, 48), (32, 48)], [(1, 1)]])
+def test_device_collate_matches_reference_collate(sizes):
+    gen = torch.Generator().manual_seed(len(sizes))
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    data = []
+    for i, (h, w) in enumerate(sizes):
+        n = [3, 0, 7][i % 3] if len(sizes) > 1 else 2
+        data.append((torch.rand(3, h, w, generator=gen), torch.rand(n, 4, generator=gen) * 50,
+                     torch.randint(1, 21, (n,), generator=gen)))
+    want = _reference_collate(data, mean, std)
+    got = P.DeviceCollate(mean, std, DEV)(data)
+    assert got[0].shape == want[0].shape and got[1].dtype == torch.float32 and got[2].dtype == torch.int64
+    assert np.array_equal(to_np(got[0]), to_np(want[0])), "normalised, padded images are not bit-exact"
+    assert np.array_equal(to_np(got[1]), to_np(want[1]))
+    assert np.array_equal(to_np(got[2]), to_np(want[2]))
+    # device-resident ragged lists take the same kernel
+    got2 = P.pack_gt([d[1].to(DEV) for d in data], [d[2].to(DEV) for d in data], DEV)
+    assert torch.equal(got2[0], got[1]) and torch.equal(got2[1], got[2])
+    # the packed batch feeds the assignment directly
+    if want[1].shape[1]:
+        a = ops.assign_targets(W.VOC_LEVELS, W.STRIDES, W.FCOS_RANGES, got[1], got[2])
+        b = O.assign_targets(W.VOC_LEVELS, want[1], want[2], W.STRIDES, W.FCOS_RANGES)
+        assert_equal_int(to_np(a[0]), to_np(b[0]))
+
+
+def test_pack_gt_empty_batch():
+    b, c = P.pack_gt([torch.zeros(0, 4), torch.zeros(0, 4)], [torch.zeros(0, dtype=torch.int64)] * 2, DEV)
+    assert b.shape == (2, 0, 4) and c.shape == (2, 0)
+
+
+# ------------------------------------------------------------------------------------------
 # full-size configs: properties that do not need the oracle at scale + oracle spot checks
 # ------------------------------------------------------------------------------------------
 def test_full_size_config2_postprocess_properties_and_oracle():
