@@ -222,6 +222,24 @@ int b200det_pack_gt(const float* flat_boxes, const int64_t* flat_labels, const i
 int b200det_collate_images(const void* const* images, const int32_t* image_hw, int batch, int channels,
                            int out_h, int out_w, const float* mean, const float* std, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * N3 — VOC average precision on the device.  Replaces sort_by_score + eval_ap_2d + _compute_ap
+ * (test.py:15-162; call site test.py:225-226) on the padded detections FCOSHead.detect() produces.
+ *   det_score [batch,max_det] f32 (descending per image), det_cls [batch,max_det] i64 (1-based),
+ *   det_box [batch,max_det,4] f32, det_count [batch] i32; gt_boxes [batch,max_gt,4] f32, gt_labels
+ *   [batch,max_gt] i64 (padding rows: label outside 1..num_cls-1, e.g. -1).
+ * `batch` is the whole evaluation set (or a rank's shard of it).  num_cls counts the background class 0,
+ * as in the reference.  Writes ap [num_cls] f64: ap[0] = 0, ap[c] = average precision of class c
+ * (NaN when the class has detections but no ground truth, as numpy's 0/0 gives; 0 without detections).
+ * A detection is a true positive iff its best-IoU ground-truth box of the same class (first index on
+ * ties) has IoU >= iou_thr and is not taken by a higher-scoring detection of the image.
+ * ------------------------------------------------------------------------------------- */
+size_t b200det_eval_ap_workspace_bytes(int batch, int max_det, int num_cls);
+int b200det_eval_ap(int batch, int max_det, int max_gt, int num_cls,
+                    const float* det_score, const int64_t* det_cls, const float* det_box,
+                    const int32_t* det_count, const float* gt_boxes, const int64_t* gt_labels,
+                    double iou_thr, void* workspace, size_t workspace_bytes, double* ap, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,3 +68,34 @@ def to_np(t):
     if isinstance(t, torch.Tensor):
         return t.detach().cpu().numpy()
     return np.asarray(t)
+
+
+def load_eval_case(name):
+    """Ragged lists + reference APs of one case of tests/golden/eval_ap.npz (made by make_golden_eval.py)."""
+    g = load_golden("eval_ap")
+
+    def ragged(key):
+        cat, off = g[f"{name}_{key}"], g[f"{name}_{key}_off"]
+        return [cat[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+    meta = g[name + "_meta"]
+    lists = {k: ragged(k) for k in ("gt_boxes", "gt_labels", "det_boxes", "det_labels", "det_scores")}
+    lists["gt_boxes"] = [np.asarray(x, dtype=np.float32).reshape(-1, 4) for x in lists["gt_boxes"]]
+    lists["det_boxes"] = [np.asarray(x, dtype=np.float32).reshape(-1, 4) for x in lists["det_boxes"]]
+    lists["gt_labels"] = [np.asarray(x, dtype=np.int64) for x in lists["gt_labels"]]
+    lists["det_labels"] = [np.asarray(x, dtype=np.int64) for x in lists["det_labels"]]
+    lists["det_scores"] = [np.asarray(x, dtype=np.float32) for x in lists["det_scores"]]
+    return lists, int(meta[2]), float(meta[5]), g[name + "_ap"]
+
+
+EVAL_CASES = ["voc_like", "coco_like", "strict_iou", "sparse"]
+
+
+def assert_ap_equal(got, want, what=""):
+    """APs are fp64 sums of a few hundred terms: equal to 1e-12, NaN where the reference gives NaN."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, f"{what}: {got.shape} vs {want.shape}"
+    assert np.array_equal(np.isnan(got), np.isnan(want)), f"{what}: NaN classes differ"
+    ok = ~np.isnan(want)
+    assert np.all(np.abs(got[ok] - want[ok]) <= 1e-12), f"{what}: worst {np.abs(got[ok] - want[ok]).max():.3e}"

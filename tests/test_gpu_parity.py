@@ -10,7 +10,8 @@ import torch
 
 from oracle import fcos_oracle as O
 from pytorch_object_detection_b200 import workloads as W
-from helpers import REL_TOL, assert_close, assert_detections_match, assert_equal_int, load_golden, to_np
+from helpers import (EVAL_CASES, REL_TOL, assert_ap_equal, assert_close, assert_detections_match, assert_equal_int,
+                     load_eval_case, load_golden, to_np)
 
 pytestmark = pytest.mark.gpu
 
@@ -606,6 +607,40 @@ def test_device_collate_matches_reference_collate(sizes):
 def test_pack_gt_empty_batch():
     b, c = P.pack_gt([torch.zeros(0, 4), torch.zeros(0, 4)], [torch.zeros(0, dtype=torch.int64)] * 2, DEV)
     assert b.shape == (2, 0, 4) and c.shape == (2, 0)
+
+
+# ------------------------------------------------------------------------------------------
+# N3: VOC average precision on the device (test.py:15-162)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_eval_ap_matches_reference_golden(name):
+    """sort_by_score + eval_ap_2d through the CUDA kernels == the reference's numpy loops (golden)."""
+    lists, num_cls, thr, want = load_eval_case(name)
+    sb, sl, ss = P.sort_by_score(lists["det_boxes"], lists["det_labels"], lists["det_scores"], DEV)
+    got = P.eval_ap_2d(lists["gt_boxes"], lists["gt_labels"], sb, sl, ss, thr, num_cls, DEV)
+    assert sorted(got) == list(range(1, num_cls))
+    assert_ap_equal([got[c] for c in range(1, num_cls)], want, what=name)
+
+
+def test_eval_ap_on_detect_outputs_large_class_and_empty():
+    """The batched entry on FCOSHead.detect() outputs against the oracle; one class with > 1024 detections
+    (several scan chunks, a sort larger than a CTA); images without detections / without ground truth."""
+    from oracle import eval_oracle as E
+    x = W.head_outputs(6, 3, W.VOC_LEVELS, seed=123)
+    head = P.FCOSHead(0.05, 0.6, 1000, W.STRIDES)
+    s, c, b, n = head.detect(cuda_levels(x), clip_hw=W.VOC_HW)
+    gt, labels = W.gt_boxes(6, 40, W.VOC_HW, 3, seed=124)
+    labels[4] = -1                                   # an image without ground truth
+    n = n.clone(); n[5] = 0                          # an image without detections
+    ap = P.eval_ap_batched(s, c, b, n, gt.to(DEV), labels.to(DEV), 0.5, 4)
+    cnt = to_np(n)
+    want = E.eval_ap([to_np(gt[i])[to_np(labels[i]) > 0] for i in range(6)],
+                     [to_np(labels[i])[to_np(labels[i]) > 0] for i in range(6)],
+                     [to_np(b[i, :cnt[i]]) for i in range(6)], [to_np(c[i, :cnt[i]]) for i in range(6)],
+                     [to_np(s[i, :cnt[i]]) for i in range(6)], 0.5, 4)
+    assert int((c[:5] == 1).sum()) > 1024
+    assert float(ap[0]) == 0.0
+    assert_ap_equal(to_np(ap)[1:], [want[k] for k in (1, 2, 3)])
 
 
 # ------------------------------------------------------------------------------------------

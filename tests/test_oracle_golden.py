@@ -132,3 +132,20 @@ def test_analytic_box_losses():
     assert float(O.iou_sum(inner, outer)) == pytest.approx(-np.log(0.25), rel=1e-6)
     with pytest.raises(NotImplementedError):
         O.reg_loss([torch.ones(1, 4, 2, 2)], torch.ones(1, 4, 4), torch.ones(1, 4, dtype=torch.bool), mode="diou")
+
+
+# ------------------------------------------------------------------------------------------
+# N3: the evaluation oracle against the reference's own eval_ap_2d (tests/golden/eval_ap.npz)
+# ------------------------------------------------------------------------------------------
+from helpers import EVAL_CASES, assert_ap_equal, load_eval_case  # noqa: E402
+from oracle import eval_oracle as E  # noqa: E402
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_eval_oracle_matches_reference_ap(name):
+    lists, num_cls, thr, want = load_eval_case(name)
+    order = [np.argsort(-s, kind="stable") for s in lists["det_scores"]]            # sort_by_score (no ties in the cases)
+    got = E.eval_ap(lists["gt_boxes"], lists["gt_labels"], [b[o] for b, o in zip(lists["det_boxes"], order)],
+                    [l[o] for l, o in zip(lists["det_labels"], order)],
+                    [s[o] for s, o in zip(lists["det_scores"], order)], thr, num_cls)
+    assert_ap_equal([got[c] for c in range(1, num_cls)], want, what=name)
