@@ -240,6 +240,14 @@ int b200det_eval_ap(int batch, int max_det, int max_gt, int num_cls,
                     const int32_t* det_count, const float* gt_boxes, const int64_t* gt_labels,
                     double iou_thr, void* workspace, size_t workspace_bytes, double* ap, void* stream);
 
+/* COCO result rows (Test_coco.py:144-168): out_xywh [batch,max_det,4] = (x1/s, y1/s, x2/s - x1/s, y2/s - y1/s)
+ * with s = scale[b] (the resize factor of image b, fp32, device), each op rounded in fp32 like numpy's
+ * in-place float32 arithmetic; out_count [batch] = number of leading detections with score >= threshold
+ * (the reference stops at the first score below it). */
+int b200det_coco_boxes(int batch, int max_det, const float* det_box, const float* det_score,
+                       const int32_t* det_count, const float* scale, float threshold,
+                       float* out_xywh, int32_t* out_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

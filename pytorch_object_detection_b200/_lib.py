@@ -54,6 +54,7 @@ PROTOTYPES = {
     "b200det_eval_ap_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "b200det_eval_ap": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_double, _P, C.c_size_t,
                                   _P, _P]),
+    "b200det_coco_boxes": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, _P, _P, _P]),
     "b200det_pack_gt": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "b200det_collate_images": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
 }

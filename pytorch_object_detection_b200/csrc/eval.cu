@@ -182,6 +182,28 @@ ap_class_kernel(const long long total, const int K, const long long* __restrict_
   if (tid == 0) ap[c] = s_ap;
 }
 
+// COCO result rows (Test_coco.py:144-168): boxes / scale, then (x, y, w, h) from the scaled corners, and per image the
+// number of leading detections with score >= threshold (the reference breaks at the first one below it).
+__global__ void __launch_bounds__(256)
+coco_boxes_kernel(const int K, const float4* __restrict__ det_box, const float* __restrict__ det_score,
+                  const int32_t* __restrict__ det_count, const float* __restrict__ scale, const float threshold,
+                  float4* __restrict__ out_xywh, int32_t* __restrict__ out_count) {
+  __shared__ int s_first;
+  const int b = blockIdx.x;
+  const int n = min(max(det_count[b], 0), K);
+  const float sc = scale[b];
+  if (threadIdx.x == 0) s_first = n;
+  __syncthreads();
+  for (int k = threadIdx.x; k < n; k += 256) {
+    const float4 v = det_box[(size_t)b * K + k];
+    const float x1 = __fdiv_rn(v.x, sc), y1 = __fdiv_rn(v.y, sc), x2 = __fdiv_rn(v.z, sc), y2 = __fdiv_rn(v.w, sc);
+    out_xywh[(size_t)b * K + k] = make_float4(x1, y1, __fsub_rn(x2, x1), __fsub_rn(y2, y1));
+    if (det_score[(size_t)b * K + k] < threshold) atomicMin(&s_first, k);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) out_count[b] = s_first;
+}
+
 }  // namespace
 }  // namespace b200det
 
@@ -230,5 +252,17 @@ extern "C" int b200det_eval_ap(int batch, int max_det, int max_gt, int num_cls, 
   if (rc) return rc;
   ap_class_kernel<<<num_cls - 1, kApThreads, 0, st>>>((long long)total, max_det, reinterpret_cast<const long long*>(det_cls),
                                                      det_score, det_count, tp, gt_total, det_total, scratch, ap);
+  return check_launch();
+}
+
+extern "C" int b200det_coco_boxes(int batch, int max_det, const float* det_box, const float* det_score,
+                                  const int32_t* det_count, const float* scale, float threshold, float* out_xywh,
+                                  int32_t* out_count, void* stream) {
+  if (batch <= 0 || batch > 65535 || max_det <= 0 || !det_box || !det_score || !det_count || !scale || !out_xywh ||
+      !out_count || !aligned16(det_box) || !aligned16(out_xywh))
+    return B200DET_ERR_ARG;
+  coco_boxes_kernel<<<batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      max_det, reinterpret_cast<const float4*>(det_box), det_score, det_count, scale, threshold,
+      reinterpret_cast<float4*>(out_xywh), out_count);
   return check_launch();
 }

@@ -643,6 +643,29 @@ def test_eval_ap_on_detect_outputs_large_class_and_empty():
     assert_ap_equal(to_np(ap)[1:], [want[k] for k in (1, 2, 3)])
 
 
+def test_coco_results_match_reference_arithmetic():
+    """Test_coco.py:144-168 restated with numpy float32 in-place ops on the same detections."""
+    x = W.head_outputs(3, 80, W.COCO_LEVELS, seed=131)
+    head = P.FCOSHead(0.05, 0.6, 1000, W.STRIDES)
+    s, c, b, n = head.detect(cuda_levels(x), clip_hw=W.COCO_HW)
+    scales = [1.6659375, 0.8, 2.0775]
+    ids, id2cat = [11, 22, 33], {k: 100 + k for k in range(1, 81)}
+    got = P.coco_results(s, c, b, n, torch.tensor(scales, device=DEV), ids, id2cat, threshold=0.3)
+    want = []
+    for i in range(3):
+        k = int(n[i])
+        boxes = to_np(b[i, :k]).copy()
+        boxes /= scales[i]
+        boxes[:, 2] -= boxes[:, 0]
+        boxes[:, 3] -= boxes[:, 1]
+        for box, score, label in zip(boxes, to_np(s[i, :k]), to_np(c[i, :k])):
+            if score < 0.3:
+                break
+            want.append({"image_id": ids[i], "category_id": id2cat[int(label)], "score": float(score), "bbox": box.tolist()})
+    assert len(got) == len(want) > 0
+    assert got == want
+
+
 # ------------------------------------------------------------------------------------------
 # full-size configs: properties that do not need the oracle at scale + oracle spot checks
 # ------------------------------------------------------------------------------------------
