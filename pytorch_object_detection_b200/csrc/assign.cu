@@ -28,7 +28,8 @@ namespace {
 
 // Tile shape (threads x points per thread), chosen per launch: small batches are dominated by the
 // per-CTA prologue, so they get wide CTAs with short tiles; large batches get more, leaner CTAs.
-// Measured on B200 (28 B written per point): <256,4> 7.2 us at B=32; <128,8> 5.0 TB/s at B=128.
+// Measured on B200 (28 B written per point): <256,6> 6.6 us at B=32 (one wave; <256,4> is 1.46 waves and
+// 7.2 us); <128,8> 5.0 TB/s at B=128.
 constexpr long long kAssignSmallPoints = 1500000;   // B*P below this -> <256,4>
 
 template <int kAssignThreads, int kAssignPts>
@@ -141,8 +142,34 @@ extern "C" int b200det_assign_targets(const int32_t* level_hw, const int32_t* st
   if (smem > 200 * 1024) return B200DET_ERR_UNSUPPORTED;
   long long total_points = 0;
   for (int l = 0; l < n_levels; ++l) total_points += (long long)level_hw[2 * l] * level_hw[2 * l + 1];
+  // Tile shape.  Small problems are a handful of waves, so the shape is chosen against WAVE QUANTISATION: a
+  // grid of 1.46 waves (config 3 with <256,4>: 864 CTAs on 592 resident slots) idles a quarter of the machine.
+  // Candidates <256 threads, 4 / 6 / 8 points>; cost model = waves * (fixed CTA latency + per-point time),
+  // constants from the phase trace (scripts/trace_assign.py): ~1.2 us fixed, ~0.21 us per point per thread.
+  // (Writing every point as a negative first, so that the store stream starts before the GT staging, and
+  // patching the positives afterwards was measured too: 8.1 us against 6.6 us — the early stores delay the
+  // GT loads behind them.)
   const bool small = (long long)batch * total_points < kAssignSmallPoints;
-  const int tile_points = small ? 256 * 4 : 128 * 8;
+  int pts = 8;
+  if (small) {
+    static int sm_count = 0;
+    if (!sm_count) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        sm_count = 148;
+    }
+    const long long slots = (long long)sm_count * 4;                   // 256 threads, <= 64 registers: 4 CTAs per SM
+    double best = 1e30;
+    for (int cand = 4; cand <= 8; cand += 2) {
+      long long tiles = 0;
+      for (int l = 0; l < n_levels; ++l)
+        tiles += ((long long)level_hw[2 * l] * level_hw[2 * l + 1] + 256 * cand - 1) / (256 * cand);
+      const long long waves = (tiles * batch + slots - 1) / slots;
+      const double cost = (double)waves * (1.2 + 0.21 * cand);
+      if (cost < best) { best = cost; pts = cand; }
+    }
+  }
+  const int tile_points = small ? 256 * pts : 128 * 8;
   AssignTable at;
   if (!make_assign_table(level_hw, strides, limit_lo, limit_hi, radius_px, n_levels, tile_points, &at))
     return B200DET_ERR_ARG;
@@ -158,7 +185,10 @@ extern "C" int b200det_assign_targets(const int32_t* level_hw, const int32_t* st
                                                      reinterpret_cast<long long*>(cls_t), cnt_t, reg_t, gt_index);
     return B200DET_OK;
   };
-  const int rc = small ? launch(assign_targets_kernel<256, 4>, 256) : launch(assign_targets_kernel<128, 8>, 128);
+  const int rc = !small     ? launch(assign_targets_kernel<128, 8>, 128)
+                 : pts == 4 ? launch(assign_targets_kernel<256, 4>, 256)
+                 : pts == 6 ? launch(assign_targets_kernel<256, 6>, 256)
+                            : launch(assign_targets_kernel<256, 8>, 256);
   if (rc) return rc;
   return check_launch();
 }
