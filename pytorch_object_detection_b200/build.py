@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200det.so")
-SOURCES = ["api.cu", "score.cu", "select.cu", "nms.cu", "fused.cu", "assign.cu", "loss.cu", "train_fused.cu", "collate.cu", "eval.cu"]
+SOURCES = ["api.cu", "score.cu", "select.cu", "nms.cu", "nms_class.cu", "fused.cu", "assign.cu", "loss.cu", "train_fused.cu", "collate.cu", "eval.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

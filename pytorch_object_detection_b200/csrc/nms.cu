@@ -22,6 +22,7 @@
 B200DET_TRACE_BUFFER(nms)
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace b200det {
 namespace {
@@ -98,42 +99,48 @@ template <bool ZERO_SUP>
 __global__ void __launch_bounds__(kNmsTile)
 nms_mask_kernel(const CandSet set, const int wblocks, const int cap_pad, const float thr_up,
                 unsigned long long* __restrict__ maskT) {
-  const int cb = blockIdx.x, rb = blockIdx.y, b = blockIdx.z;
-  if (cb < rb) return;
+  // grid = (CTAs per image, batch); a CTA strides over the image's tiles, so an image that needs no dense mask
+  // (finished by nms_class_kernel, or few candidates) costs a handful of CTAs instead of wblocks^2
+  const int b = blockIdx.y;
+  if (set.mode[b] == kModeDone) return;
   const int n = set.count[b];
-  if (rb * kNmsTile >= n || cb * kNmsTile >= n) return;
+  const int W = (n + kNmsTile - 1) / kNmsTile;                 // row / column blocks that hold candidates
   const bool same_class_only = set.mode[b] == kModeVanilla;
-
   __shared__ float4 cbox[kNmsTile];
   __shared__ float carea[kNmsTile];
   __shared__ int ccls[kNmsTile];
   const int t = threadIdx.x;
   const size_t o0 = (size_t)b * set.cap;
-  const int cj = cb * kNmsTile + t;
-  if (cj < n) {
-    const float4 v = reinterpret_cast<const float4*>(set.nms_box)[o0 + cj];
-    cbox[t] = v;
-    carea[t] = __fmul_rn(__fsub_rn(v.z, v.x), __fsub_rn(v.w, v.y));
-    ccls[t] = set.cls[o0 + cj];
-  } else {
-    // beyond the image's candidates: an inverted infinite box overlaps nothing (min(x2) = -inf is never
-    // > max(x1) = +inf) and its NaN area keeps the IoU unordered on the thr < 0 path -> bit stays 0
-    cbox[t] = make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-    carea[t] = __int_as_float(0x7fc00000);
-    ccls[t] = -1;
-  }
-  __syncthreads();
+  for (int tile = blockIdx.x; tile < W * W; tile += gridDim.x) {
+    const int rb = tile / W, cb = tile - rb * W;
+    if (cb < rb) continue;
+    __syncthreads();                                           // the previous tile's staging is no longer read
+    const int cj = cb * kNmsTile + t;
+    if (cj < n) {
+      const float4 v = reinterpret_cast<const float4*>(set.nms_box)[o0 + cj];
+      cbox[t] = v;
+      carea[t] = __fmul_rn(__fsub_rn(v.z, v.x), __fsub_rn(v.w, v.y));
+      ccls[t] = set.cls[o0 + cj];
+    } else {
+      // beyond the image's candidates: an inverted infinite box overlaps nothing (min(x2) = -inf is never
+      // > max(x1) = +inf) and its NaN area keeps the IoU unordered on the thr < 0 path -> bit stays 0
+      cbox[t] = make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+      carea[t] = __int_as_float(0x7fc00000);
+      ccls[t] = -1;
+    }
+    __syncthreads();
 
-  const int i = rb * kNmsTile + t;
-  const bool row_ok = i < n;
-  const float4 a = row_ok ? reinterpret_cast<const float4*>(set.nms_box)[o0 + i]
-                          : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-  const float aarea = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
-  const int acls = row_ok ? set.cls[o0 + i] : -2;
-  unsigned long long bits = mask_row_bits<ZERO_SUP>(a, aarea, acls, cbox, carea, ccls, thr_up, same_class_only);
-  if (cb == rb) bits &= ~((2ull << t) - 1ull);     // diagonal tile: only later boxes (j > t)
-  if (!row_ok) bits = 0ull;
-  maskT[((size_t)b * wblocks + cb) * cap_pad + i] = bits;   // 64 consecutive words per tile
+    const int i = rb * kNmsTile + t;
+    const bool row_ok = i < n;
+    const float4 a = row_ok ? reinterpret_cast<const float4*>(set.nms_box)[o0 + i]
+                            : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+    const float aarea = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    const int acls = row_ok ? set.cls[o0 + i] : -2;
+    unsigned long long bits = mask_row_bits<ZERO_SUP>(a, aarea, acls, cbox, carea, ccls, thr_up, same_class_only);
+    if (cb == rb) bits &= ~((2ull << t) - 1ull);     // diagonal tile: only later boxes (j > t)
+    if (!row_ok) bits = 0ull;
+    maskT[((size_t)b * wblocks + cb) * cap_pad + i] = bits;   // 64 consecutive words per tile
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -162,6 +169,7 @@ nms_scan_smem_kernel(const CandSet set, const int wblocks, const int cap_pad,
   constexpr int kWarps = kSmemScanThreads / 32;
   const int b = blockIdx.x;
   B200DET_STAMP_NOSYNC(16);
+  if (set.mode[b] == kModeDone) return;
   const int n = set.count[b];
   const int W = (n + kNmsTile - 1) / kNmsTile;               // <= kSmemScanMaxBlocks
   const size_t o0 = (size_t)b * set.cap;
@@ -276,6 +284,7 @@ nms_scan_ring_kernel(const CandSet set, const int wblocks, const int cap_pad,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = kRingThreads / 32;
   const int b = blockIdx.x;
+  if (set.mode[b] == kModeDone) return;
   const int n = set.count[b];
   const int W = (n + kNmsTile - 1) / kNmsTile;
   const int slot_words = wblocks * kNmsTile;
@@ -398,11 +407,22 @@ int launch_nms(const CandSet& set, int batch, double nms_thr, int clip_h, int cl
   nms_threshold_params(nms_thr, &thr_up, &zero_suppresses);
   const int wblocks = nms_blocks(set.cap);
   const int cap_pad = wblocks * kNmsTile;
+  int rc;
+  // Above 1000 candidates an image is in torchvision's per-class mode: nms_class_kernel finishes those images
+  // (unless a class is larger than it handles) and the dense kernels below only see what is left.
+  static const bool no_class = getenv("B200DET_NO_CLASS_NMS") && getenv("B200DET_NO_CLASS_NMS")[0] == '1';
+  if (set.cap * 4 > kTrickMaxNumel && !no_class) {
+    rc = launch_nms_class(set, batch, thr_up, zero_suppresses, clip_h, clip_w, out, stream);
+    if (rc) return rc;
+  }
+  // CTAs per image: every upper-triangle tile its own CTA up to a few waves of the machine, strided beyond
+  const int tri = wblocks * (wblocks + 1) / 2;
+  const int per_image = tri < 4096 ? tri : 4096;
   if (zero_suppresses)
-    nms_mask_kernel<true><<<dim3(wblocks, wblocks, batch), kNmsTile, 0, stream>>>(set, wblocks, cap_pad, thr_up, mask);
+    nms_mask_kernel<true><<<dim3(per_image, batch), kNmsTile, 0, stream>>>(set, wblocks, cap_pad, thr_up, mask);
   else
-    nms_mask_kernel<false><<<dim3(wblocks, wblocks, batch), kNmsTile, 0, stream>>>(set, wblocks, cap_pad, thr_up, mask);
-  int rc = check_launch();
+    nms_mask_kernel<false><<<dim3(per_image, batch), kNmsTile, 0, stream>>>(set, wblocks, cap_pad, thr_up, mask);
+  rc = check_launch();
   if (rc) return rc;
   if (wblocks <= kSmemScanMaxBlocks) {
     const size_t smem = (size_t)kNmsTile * (wblocks * (wblocks + 1) / 2) * sizeof(unsigned long long);

@@ -6,6 +6,7 @@ namespace b200det {
 
 constexpr int kModeTrick = 0;     // torchvision _batched_nms_coordinate_trick (numel <= 4000 on CPU)
 constexpr int kModeVanilla = 1;   // torchvision _batched_nms_vanilla (per class, raw boxes)
+constexpr int kModeDone = 2;      // vanilla image already finished by nms_class_kernel: the dense kernels skip it
 constexpr int kTrickMaxNumel = 4000;
 
 // Per image `count[b]` candidates in stable descending score order, row stride `cap`.
@@ -66,6 +67,10 @@ int launch_fused_select_nms(const LevelTable& lt, int batch, const float* score,
 // candidate set + suppression mask carved out of one caller-owned workspace
 size_t nms_set_workspace_bytes(int batch, int cap);
 void nms_set_carve(void* base, int batch, int cap, CandSet* set, unsigned long long** mask);
+
+// per-class path for vanilla images (nms_class.cu); marks the images it finishes kModeDone
+int launch_nms_class(const CandSet& set, int batch, float thr_up, bool zero_sup, int clip_h, int clip_w,
+                     const NmsOut& out, cudaStream_t stream);
 
 int launch_nms(const CandSet& set, int batch, double nms_thr, int clip_h, int clip_w,
                unsigned long long* mask, const NmsOut& out, cudaStream_t stream);

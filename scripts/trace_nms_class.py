@@ -1,0 +1,18 @@
+"""Phase timing of nms_class_kernel on the dense-crowd case (needs a B200DET_TRACE=1 build)."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from pytorch_object_detection_b200 import _lib, ops, workloads as W
+lib = _lib.load()
+crowd = [W.crowd_candidates(5000, 80, seed=400 + i) for i in range(8)]
+cb = torch.stack([c[0] for c in crowd]).cuda(); cs = torch.stack([c[1] for c in crowd]).cuda(); cc = torch.stack([c[2] for c in crowd]).cuda()
+for _ in range(3):
+    ops.batched_nms(cb, cs, cc, 0.05, 0.6)
+torch.cuda.synchronize()
+buf = (C.c_longlong * 64)()
+fn = lib.b200det_debug_read_trace_nmsclass
+fn.argtypes = [C.c_void_p, C.c_int]
+fn(buf, 64)
+t = list(buf)
+names = ["keys", "sort", "segments", "class warps", "write"]
+print(" ".join(f"{n} +{(t[i + 1] - t[i]) / 1965:.1f}us" for i, n in enumerate(names)), "segments", t[8])

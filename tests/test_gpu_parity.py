@@ -134,7 +134,10 @@ def test_nms_matches_torchvision_golden():
 
 
 @pytest.mark.parametrize("seed,n,ncls", [(1, 300, 4), (2, 999, 80), (3, 1000, 20), (4, 1500, 10), (5, 64, 2),
-                                         (6, 65, 2), (7, 2048, 3), (8, 5000, 80)])
+                                         (6, 65, 2), (7, 2048, 3), (8, 5000, 80),
+                                         # per-class path: one class larger than a warp handles (dense fallback),
+                                         # a single class just above / below that limit, many tiny classes
+                                         (9, 3000, 2), (10, 1200, 1), (11, 1001, 1), (12, 4100, 1000), (13, 8192, 80)])
 def test_nms_matches_oracle_random(seed, n, ncls):
     boxes, scores, classes = W.crowd_candidates(n, ncls, seed=seed, clusters=8)
     boxes[::7] -= 600.0          # negative coordinates: cross-class suppression on the trick branch
