@@ -405,6 +405,25 @@ def main():
             loss.backward()
             return loss
 
+        clss = [[(torch.randn(TRAIN_BATCH, NCLS, h, w, device=dev) - 4.595).requires_grad_(True)
+                 for h, w in W.COCO_LEVELS] for _ in range(2)]
+
+        def train_step_full(i):
+            """The whole FCOSGenTargets + FCOSLoss step: fused assign/box/centerness launch + one focal launch that
+            writes the loss and the 238 MB class gradient from one read of the logits."""
+            for t in regs[i % 4] + cnts[i % 4] + clss[i % 2]:
+                t.grad = None
+            fused([(clss[i % 2], cnts[i % 4], regs[i % 4]), gt, labels])[3].backward()
+
+        def train_step_full_two_focal_kernels(i):
+            """Same step with the focal loss as separate forward and backward kernels (logits read twice)."""
+            for t in regs[i % 4] + cnts[i % 4] + clss[i % 2]:
+                t.grad = None
+            reg_loss, cnt_loss = fused.box_cnt_losses(cnts[i % 4], regs[i % 4], gt, labels)
+            cls_t, cnt_t, _ = fused.targets
+            cls_loss = B.compute_cls_loss(clss[i % 2], cls_t, None, _mask_src=cnt_t).mean()
+            (cls_loss + cnt_loss + reg_loss).backward()
+
         def timed_graph(fn, reps):
             """us per call of fn(i), captured as one CUDA graph of 4 calls (no Python between launches)."""
             for i in range(4):
@@ -437,6 +456,10 @@ def main():
             us_unfused = timed_graph(train_step_unfused, args.steps)
             us_kernels = timed_graph(lambda i: ops.assign_loss_fused(regs[i % 4], None, W.STRIDES, W.HISFCOS_RANGES,
                                                                     gt, labels, 1), args.steps)
+            us_full = timed_graph(train_step_full, args.steps)
+            us_full_two = timed_graph(train_step_full_two_focal_kernels, args.steps)
+            us_focal = timed_graph(lambda i: ops.cls_loss_step(clss[i % 2], fused.targets[0],
+                                                               num_pos=fused.per_image["num_pos"]), args.steps)
             # assign alone, for its own roofline: 28 bytes written per point
             us_assign = timed_graph(
                 lambda i: ops.assign_targets(W.COCO_LEVELS, W.STRIDES, W.HISFCOS_RANGES, gt, labels), args.steps)
@@ -448,6 +471,12 @@ def main():
                  "fused_gbs": fused_bytes / (us_kernels * 1e-6) / 1e9,
                  "fused_frac_of_peak": fused_bytes / (us_kernels * 1e-6) / 1e9 / peak,
                  "with_centerness_us": us_cnt, "unfused_us_per_batch": us_unfused,
+                 "full_step": {"what": "targets + focal + centerness + GIoU losses and all gradients (FCOSTargetLoss "
+                                       "forward + total.backward())",
+                               "us_per_batch": us_full, "us_with_two_focal_kernels": us_full_two,
+                               "focal_step_kernel_us": us_focal, "focal_bytes": 2 * TRAIN_BATCH * P * NCLS * 4,
+                               "focal_gbs": 2 * TRAIN_BATCH * P * NCLS * 4 / (us_focal * 1e-6) / 1e9,
+                               "focal_frac_of_peak": 2 * TRAIN_BATCH * P * NCLS * 4 / (us_focal * 1e-6) / 1e9 / peak},
                  "assign_us": us_assign, "assign_bytes": assign_bytes,
                  "assign_gbs": assign_bytes / (us_assign * 1e-6) / 1e9,
                  "assign_frac_of_peak": assign_bytes / (us_assign * 1e-6) / 1e9 / peak}

@@ -167,6 +167,20 @@ int b200det_cls_loss_bwd(const b200det_level* levels, float* const* grads, int n
                          int num_classes, const int64_t* cls_t,
                          const float* grad_loss, const float* num_pos, void* stream);
 
+/* The focal loss of a TRAINING STEP: loss and gradient from ONE read of the class logits
+ * (compute_cls_loss forward, loss.py:6-26, and its autograd backward; the `.mean()` of loss.py:210).
+ *   grads[l] [B,C,h,w] receive d(sum_b grad_loss[b] * loss[b]) / d(cls level l);
+ *   grad_loss [B] f32 device, or NULL for 1/B each (the gradient of the batch mean);
+ *   num_pos [B] f32: read when num_pos_ready != 0 (as b200det_assign_loss_fused / *_loss_fwd wrote it),
+ *     otherwise computed first from cnt_t (> -1 marks a positive) and written;
+ *   loss [B] f32 = focal sum / num_pos; mean_out [1] f32 or NULL = batch mean, added in image order.
+ * workspace: b200det_cls_loss_workspace_bytes(). */
+int b200det_cls_loss_step(const b200det_level* levels, float* const* grads, int n_levels, int batch,
+                          int num_classes, const int64_t* cls_t, const float* cnt_t,
+                          const float* grad_loss, int num_pos_ready,
+                          void* workspace, size_t workspace_bytes,
+                          float* loss, float* num_pos, float* mean_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * K4 fused: one launch per training step for
  *   FCOSGenTargets.forward (head.py:218-316)

@@ -23,7 +23,7 @@ launch_count = 0          # kernels launched through this module (bench.py repor
 # kernels per C entry point (see csrc/*.cu)
 _LAUNCHES = {"postprocess": 4, "batched_nms": 3, "score_points": 1, "select_topk": 1, "clip_boxes": 1,
              "assign_targets": 1, "box_loss_fwd": 1, "box_loss_bwd": 1, "cnt_loss_fwd": 1, "cnt_loss_bwd": 1,
-             "cls_loss_fwd": 2, "cls_loss_bwd": 1, "assign_loss_fused": 3, "scale_maps": 1,
+             "cls_loss_fwd": 2, "cls_loss_bwd": 1, "cls_loss_step": 2, "count_pos": 1, "assign_loss_fused": 3, "scale_maps": 1,
              "pack_gt": 1, "collate_images": 1, "eval_ap": 2, "coco_boxes": 1}
 
 
@@ -428,6 +428,43 @@ def cls_loss_bwd(cls: Sequence[Tensor], cls_t: Tensor, grad_loss: Tensor, npos: 
     _lib.check(rc, "b200det_cls_loss_bwd")
     _count("cls_loss_bwd")
     return grads
+
+
+def cls_loss_step(cls: Sequence[Tensor], cls_t: Tensor, mask_src: Tensor | None = None,
+                  num_pos: Tensor | None = None, grad_loss: Tensor | None = None):
+    """compute_cls_loss forward AND backward from one read of the logits (b200det_cls_loss_step).
+
+    ``num_pos`` [B] (from the fused assignment step) or ``mask_src`` (cnt_t, > -1 = positive) must be given.
+    Returns (loss [B], mean [1], num_pos [B], grads) with grads = d(sum_b grad_loss[b] * loss[b]) / d(cls maps),
+    grad_loss defaulting to 1/B (the gradient of the batch mean)."""
+    lib = _lib.load()
+    lv, keep_alive, p_total, batch, n = _levels(cls, None, None, [1] * len(cls))
+    dev = keep_alive[0].device
+    _need_cuda(cls_t, "cls target")
+    t = cls_t.to(torch.int64).reshape(batch, -1).contiguous()
+    assert t.shape[1] == p_total
+    if num_pos is None and mask_src is None:
+        raise _lib.B200DetError("cls_loss_step needs num_pos or the positive-mask source (cnt_t)")
+    m = _mask_src(mask_src, batch, p_total) if num_pos is None else None
+    ready = num_pos is not None
+    npos = _f32c(num_pos, "num_pos").reshape(batch) if ready else torch.empty((batch,), dtype=torch.float32, device=dev)
+    gl = _f32c(grad_loss, "grad_loss").reshape(batch) if grad_loss is not None else None
+    c = keep_alive[0].shape[1]
+    ws_bytes = lib.b200det_cls_loss_workspace_bytes(batch, p_total, c)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    loss = torch.empty((batch,), dtype=torch.float32, device=dev)
+    mean = torch.empty((1,), dtype=torch.float32, device=dev)
+    grads = [torch.empty_like(x) for x in keep_alive]
+    ptr = lambda x: x.data_ptr() if x is not None else None
+    with torch.cuda.device(dev):
+        rc = lib.b200det_cls_loss_step(lv, _grad_ptrs(grads), n, batch, c, t.data_ptr(), ptr(m), ptr(gl), int(ready),
+                                       ws.data_ptr(), ws_bytes, loss.data_ptr(), npos.data_ptr(), mean.data_ptr(),
+                                       _stream(t))
+    _lib.check(rc, "b200det_cls_loss_step")
+    _count("cls_loss_step")
+    if not ready:
+        _count("count_pos")        # the positive count kernel ran first
+    return loss, mean, npos, grads
 
 
 # --------------------------------------------------------------------------------------------

@@ -63,6 +63,7 @@ cases = {
     "cnt_loss_bwd": lambda i: ops.cnt_loss_bwd(tsets[i % 2][1], tgt[1], tgt[1], gl, npos),
     "cls_loss_fwd": lambda i: ops.cls_loss_fwd(tsets[i % 2][0], tgt[1], tgt[0]),
     "cls_loss_bwd": lambda i: ops.cls_loss_bwd(tsets[i % 2][0], tgt[0], gl, npos),
+    "cls_loss_step": lambda i: ops.cls_loss_step(tsets[i % 2][0], tgt[0], num_pos=npos),
 }
 only = [s for s in args.only.split(",") if s]
 for name, fn in cases.items():

@@ -420,6 +420,71 @@ def test_fused_target_loss_matches_reference(name, mode):
     for lv in range(len(levels)):
         assert_close(to_np(xc[2][lv].grad), g[f"g_reg_{mode}_{lv}"], rel=REL_TOL, abs_=1e-9, what=f"g_reg {lv}")
         assert_close(to_np(xc[1][lv].grad), g[f"g_cnt_{mode}_{lv}"], rel=REL_TOL, abs_=1e-9, what=f"g_cnt {lv}")
+        if f"g_cls_{mode}_{lv}" in g.files:
+            assert_close(to_np(xc[0][lv].grad), g[f"g_cls_{mode}_{lv}"], rel=REL_TOL, abs_=1e-12, what=f"g_cls {lv}")
+        else:
+            assert_close(to_np(xc[0][lv].grad.double().sum(dim=(2, 3))), g[f"g_cls_sum_{mode}_{lv}"], rel=1e-4,
+                         abs_=1e-9, what=f"g_cls sums {lv}")
+
+
+def test_focal_step_wide_logit_range_odd_levels_and_upstream_scale():
+    """b200det_cls_loss_step (loss + gradient from one read of the logits) over logits in [-30, 14], on levels
+    that take the 128-bit path, the scalar path (13x21) and a ragged last tile, with C = 21 (class-chunk
+    remainder of 5 = one 4-plane group + one slow plane), against the reference formula under CPU autograd
+    (loss.py:6-26, 180-193); then FCOSLoss with a non-unit upstream gradient against the two-kernel path.
+
+    Gradient floor: the reference forms om = 1 - fl(1 - p), a multiple of 2^-24.  A 1-ulp difference between
+    torch's CPU sigmoid and the kernel's moves fl(1 - p) by one step on ~1 % of the elements, i.e. om by 6e-8
+    ABSOLUTE; the gradient is ~2.25 om^3, so that step alone is 4e-7 om^2 — above 1e-5 relative for om < 0.05
+    and below 1e-9 in absolute terms.  Same floor as test_focal_wide_logit_range, times the gradient scale."""
+    gen = torch.Generator().manual_seed(17)
+    B, C = 3, 21
+    levels = [(40, 52), (13, 21), (7, 12), (1, 3)]
+    P_total = sum(h * w for h, w in levels)
+    cls = []
+    for h, w in levels:
+        n = B * C * h * w
+        v = torch.cat([torch.linspace(-30, 14, n // 2), (torch.rand(n - n // 2, generator=gen) - 0.5) * 16])
+        cls.append(v[torch.randperm(n, generator=gen)].reshape(B, C, h, w))
+    cls_t = torch.zeros(B, P_total, 1, dtype=torch.int64)
+    pos = torch.rand(B, P_total, generator=gen) < 0.03
+    pos[2] = False                                                       # an image without positives: num_pos clamps to 1
+    cls_t[pos] = torch.randint(1, C + 1, (int(pos.sum()), 1), generator=gen)
+    cnt_t = torch.where(pos, 0.5, -1.0).reshape(B, P_total, 1)
+    ref_in = [t.clone().requires_grad_(True) for t in cls]
+    want = O.cls_loss(ref_in, cls_t, pos)
+    want.mean().backward()
+    a = [t.clone().to(DEV).requires_grad_(True) for t in cls]
+    loss, mean, npos, grads = ops.cls_loss_step(a, cls_t.to(DEV), mask_src=cnt_t.to(DEV))
+    assert_close(to_np(loss), to_np(want), rel=REL_TOL, what="per-image focal loss")
+    assert_close(float(mean), float(want.mean()), rel=REL_TOL)
+    assert_equal_int(to_np(npos), np.maximum(to_np(pos.sum(dim=1)), 1))
+    for gpu, ref in zip(grads, ref_in):
+        assert_close(to_np(gpu), to_np(ref.grad), rel=REL_TOL, abs_=1e-9 / B, what="focal step gradient")
+    # num_pos handed in (the fused assignment made it) + per-image upstream gradients
+    up = torch.tensor([0.25, 2.0, -1.0])
+    _, _, _, grads2 = ops.cls_loss_step(a, cls_t.to(DEV), num_pos=npos, grad_loss=up.to(DEV))
+    for t in ref_in:
+        t.grad = None
+    (O.cls_loss(ref_in, cls_t, pos) * up).sum().backward()
+    for gpu, ref in zip(grads2, ref_in):
+        assert_close(to_np(gpu), to_np(ref.grad), rel=REL_TOL, abs_=2e-9, what="focal step gradient, upstream")
+    # through the modules: FCOSLoss (gradient written by the forward kernel, rescaled in backward) == two kernels
+    cnt = [torch.randn(B, 1, h, w, generator=gen).to(DEV).requires_grad_(True) for h, w in levels]
+    reg = [torch.exp(torch.randn(B, 4, h, w, generator=gen)).to(DEV).requires_grad_(True) for h, w in levels]
+    reg_t = torch.where(pos[..., None], torch.rand(B, P_total, 4, generator=gen) * 50 + 1, -1.0)
+    tgt = (cls_t.to(DEV), cnt_t.to(DEV), reg_t.to(DEV))
+    losses = P.FCOSLoss("giou")([(a, cnt, reg), tgt])
+    (2.5 * losses[3]).backward()
+    two = P.compute_cls_loss([t.detach().clone().requires_grad_(True) for t in a], tgt[0], None, _mask_src=tgt[1])
+    assert_close(float(losses[0]), float(two.mean()), rel=REL_TOL)
+    b2 = [t.detach().clone().requires_grad_(True) for t in a]
+    (2.5 * P.compute_cls_loss(b2, tgt[0], None, _mask_src=tgt[1]).mean()).backward()
+    for x, y in zip(a, b2):
+        assert_close(to_np(x.grad), to_np(y.grad), rel=REL_TOL, abs_=1e-12, what="FCOSLoss cls gradient")   # same sigmoid
+    with torch.no_grad():                                                # no gradient asked for: forward kernel only
+        l0 = P.FCOSLoss("giou")([(a, cnt, reg), tgt])[0]
+    assert_close(float(l0), float(losses[0]), rel=REL_TOL)
 
 
 def test_fused_target_loss_equals_unfused_kernels_full_size_and_upstream_scale():
