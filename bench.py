@@ -405,8 +405,7 @@ def main():
             loss.backward()
             return loss
 
-        clss = [[(torch.randn(TRAIN_BATCH, NCLS, h, w, device=dev) - 4.595).requires_grad_(True)
-                 for h, w in W.COCO_LEVELS] for _ in range(2)]
+        clss = []            # two sets of class logits (238 MB each), made when the full step is timed
 
         def train_step_full(i):
             """The whole FCOSGenTargets + FCOSLoss step: fused assign/box/centerness launch + one focal launch that
@@ -456,6 +455,8 @@ def main():
             us_unfused = timed_graph(train_step_unfused, args.steps)
             us_kernels = timed_graph(lambda i: ops.assign_loss_fused(regs[i % 4], None, W.STRIDES, W.HISFCOS_RANGES,
                                                                     gt, labels, 1), args.steps)
+            clss.extend([(torch.randn(TRAIN_BATCH, NCLS, h, w, device=dev) - 4.595).requires_grad_(True)
+                          for h, w in W.COCO_LEVELS] for _ in range(2))
             us_full = timed_graph(train_step_full, args.steps)
             us_full_two = timed_graph(train_step_full_two_focal_kernels, args.steps)
             us_focal = timed_graph(lambda i: ops.cls_loss_step(clss[i % 2], fused.targets[0],

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200DET_ABI_VERSION 4
+#define B200DET_ABI_VERSION 5
 #define B200DET_MAX_LEVELS 8
 #define B200DET_MAX_BOX 8192      /* largest max_detection_box / NMS candidate count per image */
 
@@ -35,6 +35,13 @@ typedef enum {
   B200DET_ERR_WORKSPACE = 3,      /* workspace smaller than *_workspace_bytes() */
   B200DET_ERR_CUDA = 4            /* a launch failed; see b200det_last_cuda_error() */
 } b200det_status;
+
+/* element type of a map that may be something else than fp32 */
+typedef enum {
+  B200DET_F32 = 0,
+  B200DET_F16 = 1,
+  B200DET_BF16 = 2
+} b200det_dtype;
 
 /* One FPN level of head outputs: cls [B,C,h,w], cnt [B,1,h,w], reg [B,4,h,w], fp32 (any may
  * be NULL where an entry point does not read it).  reg holds the (l, t, r, b) distances, or — when
@@ -170,14 +177,15 @@ int b200det_cls_loss_bwd(const b200det_level* levels, float* const* grads, int n
 /* The focal loss of a TRAINING STEP: loss and gradient from ONE read of the class logits
  * (compute_cls_loss forward, loss.py:6-26, and its autograd backward; the `.mean()` of loss.py:210).
  *   grads[l] [B,C,h,w] receive d(sum_b grad_loss[b] * loss[b]) / d(cls level l);
- *   grad_loss [B] f32 device, or NULL for 1/B each (the gradient of the batch mean);
+ *   grad_loss: NULL for 1/B each (the gradient of the batch mean); grad_mode 0: [B] f32 device, dL/d(loss[b]);
+ *     grad_mode 1: ONE f32 device value, the upstream gradient of the batch MEAN (a loss scale) -> /B each;
  *   num_pos [B] f32: read when num_pos_ready != 0 (as b200det_assign_loss_fused / *_loss_fwd wrote it),
  *     otherwise computed first from cnt_t (> -1 marks a positive) and written;
  *   loss [B] f32 = focal sum / num_pos; mean_out [1] f32 or NULL = batch mean, added in image order.
  * workspace: b200det_cls_loss_workspace_bytes(). */
 int b200det_cls_loss_step(const b200det_level* levels, float* const* grads, int n_levels, int batch,
                           int num_classes, const int64_t* cls_t, const float* cnt_t,
-                          const float* grad_loss, int num_pos_ready,
+                          const float* grad_loss, int grad_mode, int num_pos_ready,
                           void* workspace, size_t workspace_bytes,
                           float* loss, float* num_pos, float* mean_out, void* stream);
 
@@ -194,7 +202,8 @@ int b200det_cls_loss_step(const b200det_level* levels, float* const* grads, int 
  *   levels[l].reg (+ .cnt when cnt_grads != NULL), h, w, stride : head outputs (read at positives)
  *   reg_grads[l] [B,4,h,w], cnt_grads[l] [B,1,h,w] (host arrays of device pointers; cnt_grads may be
  *     NULL together with cnt_loss): receive d(sum_b grad_*[b] * loss[b]) / d(map), zeros off positives
- *   grad_box / grad_cnt [B] f32 device, or NULL for 1/B each (the gradient of the batch mean)
+ *   grad_box / grad_cnt: NULL for 1/B each (the gradient of the batch mean); grad_mode 0: [B] f32 device;
+ *     grad_mode 1: ONE f32 device value each, the upstream gradient of the batch mean (divided by B inside)
  *   cls_t / cnt_t / reg_t : the targets, as b200det_assign_targets writes them (bit-identical)
  *   box_loss / cnt_loss / num_pos [B] f32 : as b200det_box_loss_fwd / b200det_cnt_loss_fwd
  *   mean_out [2] f32 or NULL : batch means of box_loss and cnt_loss, added in image order
@@ -208,7 +217,7 @@ int b200det_assign_loss_fused(const b200det_level* levels, float* const* reg_gra
                               int n_levels, const float* limit_lo, const float* limit_hi,
                               const float* radius_px, int batch, int max_gt,
                               const float* gt_boxes, const int64_t* gt_labels, int mode,
-                              const float* grad_box, const float* grad_cnt,
+                              const float* grad_box, const float* grad_cnt, int grad_mode,
                               int64_t* cls_t, float* cnt_t, float* reg_t,
                               float* box_loss, float* cnt_loss, float* num_pos, float* mean_out,
                               float* reg_scale_grad, void* workspace, size_t workspace_bytes, void* stream);
@@ -218,6 +227,19 @@ int b200det_assign_loss_fused(const b200det_level* levels, float* const* reg_gra
  * backward of the fused step: its gradients are final unless the upstream gradient differs from 1. */
 int b200det_scale_maps(float* const* maps, const int64_t* numel, const float* const* factors, int n_maps,
                        void* stream);
+
+/* The autograd backward of b200det_assign_loss_fused / b200det_cls_loss_step when their gradients were
+ * written for an ASSUMED upstream gradient (grad_mode 1).  A `state` is TWO consecutive fp32 words on the
+ * device: {assumed upstream gradient, 0} (the second word is a ticket the kernel uses and resets); the
+ * forward entry points take a pointer to its first word.  got[s] is the upstream gradient that arrived for
+ * state s.  Map i (numel[i] elements of `dtype`) belongs to state state_of[i]: if *got != assumed the map is
+ * multiplied by *got / assumed in place, otherwise it is not touched; afterwards assumed = *got (unless that
+ * is 0 or not finite), so that the next forward assumes the upstream gradient this backward received — under
+ * torch.cuda.amp.GradScaler (train.py:127,180) that is the loss scale, constant for thousands of steps.
+ * One launch.  maps / numel / state_of (n_maps <= 16) and got / state (n_states <= 4, each state listed once)
+ * are HOST arrays. */
+int b200det_rescale_maps(void* const* maps, const int64_t* numel, const int32_t* state_of, int dtype, int n_maps,
+                         const float* const* got, float* const* state, int n_states, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * N4 — the datasets' collate_fn on the device (dataset/voc.py:141-173, dataset/coco.py:135-165).

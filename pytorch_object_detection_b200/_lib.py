@@ -14,7 +14,7 @@ from . import build as _build
 
 MAX_LEVELS = 8
 MAX_BOX = 8192
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class Level(C.Structure):
@@ -47,12 +47,13 @@ PROTOTYPES = {
     "b200det_cls_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "b200det_cls_loss_fwd": (C.c_int, [_LV, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P, _P, _P]),
     "b200det_cls_loss_bwd": (C.c_int, [_LV, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
-    "b200det_cls_loss_step": (C.c_int, [_LV, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, C.c_size_t,
+    "b200det_cls_loss_step": (C.c_int, [_LV, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, C.c_size_t,
                                         _P, _P, _P, _P]),
     "b200det_assign_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "b200det_assign_loss_fused": (C.c_int, [_LV, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int,
-                                            _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+                                            _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "b200det_scale_maps": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "b200det_rescale_maps": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     "b200det_eval_ap_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "b200det_eval_ap": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_double, _P, C.c_size_t,
                                   _P, _P]),

@@ -40,6 +40,13 @@ struct GradTable {
   float* g[B200DET_MAX_LEVELS];
 };
 
+// Upstream gradient dL/d(loss[b]) of image b.  grad NULL: 1/B (the gradient of the batch mean for an upstream
+// of 1); grad_mode 0: grad[b]; grad_mode 1: grad[0] is the upstream gradient of the batch MEAN -> grad[0] / B.
+__device__ __forceinline__ float upstream_of(const float* grad, const int grad_mode, const int b, const float inv_batch) {
+  if (!grad) return inv_batch;
+  return grad_mode ? __ldcg(grad) * inv_batch : grad[b];
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // Returns false on bad arguments.

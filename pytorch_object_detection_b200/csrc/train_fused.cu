@@ -135,7 +135,8 @@ template <bool kScaleExp>                      // some level carries a folded Sc
 __global__ void __launch_bounds__(kTrainThreads, 3)
 assign_loss_tile_kernel(const AssignTable at, const LossMaps lm, const int has_cnt, const int M,
                         const float* __restrict__ gt_boxes, const long long* __restrict__ gt_labels, const int mode,
-                        const float* __restrict__ grad_box, const float* __restrict__ grad_cnt, const float inv_batch,
+                        const float* __restrict__ grad_box, const float* __restrict__ grad_cnt, const int grad_mode,
+                        const float inv_batch,
                         const float* num_pos, long long* __restrict__ cls_t, float* __restrict__ cnt_t,
                         float* __restrict__ reg_t, float* partial, const int use_pdl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -281,8 +282,8 @@ assign_loss_tile_kernel(const AssignTable at, const LossMaps lm, const int has_c
   if (use_pdl) pdl_wait();                       // count_positives_kernel has completed and is visible
   if (pos_mask) {
     const float np = __ldcg(num_pos + b);
-    const float scale_box = (grad_box ? grad_box[b] : inv_batch) / np;
-    const float scale_cnt = (grad_cnt ? grad_cnt[b] : inv_batch) / np;
+    const float scale_box = upstream_of(grad_box, grad_mode, b, inv_batch) / np;
+    const float scale_cnt = upstream_of(grad_cnt, grad_mode, b, inv_batch) / np;
 #pragma unroll
     for (int q = 0; q < kTrainPts; ++q) {
       if (!(pos_mask & (1u << q))) continue;
@@ -325,8 +326,8 @@ struct TileLevels {
 
 __global__ void __launch_bounds__(kFinalThreads)
 finalize_losses_kernel(const int batch, const int n_tiles, const TileLevels tl, const float* __restrict__ partial,
-                       const float* __restrict__ num_pos, const float* __restrict__ grad_box, const float inv_batch,
-                       float* __restrict__ box_loss, float* __restrict__ cnt_loss, float* __restrict__ mean_out,
+                       const float* __restrict__ num_pos, const float* __restrict__ grad_box, const int grad_mode,
+                       const float inv_batch, float* __restrict__ box_loss, float* __restrict__ cnt_loss, float* __restrict__ mean_out,
                        float* __restrict__ reg_scale_grad, const int use_pdl) {
   __shared__ float4 stage[kFinalStage];
   __shared__ float2 img[kFinalImages];
@@ -343,7 +344,7 @@ finalize_losses_kernel(const int batch, const int n_tiles, const TileLevels tl, 
     __syncthreads();
     for (int i = tid; i < n; i += kFinalThreads) {
       const float np = __ldcg(num_pos + i0 + i);
-      const float up = (grad_box ? grad_box[i0 + i] : inv_batch) / np;
+      const float up = upstream_of(grad_box, grad_mode, i0 + i, inv_batch) / np;
       float tb = 0.f, tc = 0.f;
       for (int l = 0; l < tl.n_levels; ++l) {
         float td = 0.f;
@@ -380,7 +381,7 @@ finalize_losses_kernel(const int batch, const int n_tiles, const TileLevels tl, 
 // In-place multiply of up to kMaxScaleMaps arrays, each by its own device scalar; a map whose scalar is
 // exactly 1 costs nothing (the usual case: the fused kernel already applied d(mean)/d(loss[b]) = 1/B
 // and backward() feeds 1).
-constexpr int kMaxScaleMaps = 2 * B200DET_MAX_LEVELS;
+constexpr int kMaxScaleMaps = 16;
 struct ScaleTable {
   float* map[kMaxScaleMaps];
   const float* factor[kMaxScaleMaps];
@@ -393,6 +394,72 @@ __global__ void __launch_bounds__(256) scale_maps_kernel(const ScaleTable t) {
   float* m = t.map[blockIdx.y];
   const long long n = t.numel[blockIdx.y];
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) m[i] *= f;
+}
+
+// Autograd backward of the eager-gradient steps (the forward kernels wrote final gradients for an ASSUMED
+// upstream gradient): map *= got / assumed, skipped entirely when the two are equal — which they are from the
+// second step on, because the assumed value is then overwritten with the one that arrived (a GradScaler's loss
+// scale is constant for thousands of steps).  ONE launch of a fixed, small grid (the usual case is the no-op):
+// every CTA walks all maps with 128-bit accesses; the last CTA to finish (a ticket next to each assumed value)
+// stores the new assumption, after every CTA has consumed the old one.
+constexpr int kMaxStates = 4;
+constexpr int kRescaleCtas = 74;             // the usual launch is a no-op: keep it small
+struct RescaleTable {
+  void* map[kMaxScaleMaps];
+  long long numel[kMaxScaleMaps];
+  int state_of[kMaxScaleMaps];
+  const float* got[kMaxStates];
+  float* state[kMaxStates];                  // {assumed upstream gradient, ticket (as bits of an unsigned)}
+};
+
+__global__ void __launch_bounds__(256) rescale_maps_kernel(const RescaleTable t, const int n_maps, const int n_states) {
+  __shared__ float s_f[kMaxStates];
+  if (threadIdx.x < n_states) {
+    const float got = __ldcg(t.got[threadIdx.x]), assumed = __ldcg(t.state[threadIdx.x]);
+    s_f[threadIdx.x] = (got == assumed) ? 1.0f : got / assumed;
+  }
+  __syncthreads();
+  const long long step = (long long)gridDim.x * 256;
+  const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
+  for (int i = 0; i < n_maps; ++i) {
+    const float f = s_f[t.state_of[i]];
+    if (f == 1.0f) continue;
+    float* m = static_cast<float*>(t.map[i]);
+    const long long n = t.numel[i];
+    if ((reinterpret_cast<uintptr_t>(m) & 15u) == 0) {
+      float4* m4 = reinterpret_cast<float4*>(m);
+      const long long n4 = n / 4;
+      long long j = i0;
+      for (; j + 3 * step < n4; j += 4 * step) {                 // four 128-bit loads in flight per thread
+        float4 v0 = m4[j], v1 = m4[j + step], v2 = m4[j + 2 * step], v3 = m4[j + 3 * step];
+        v0.x *= f; v0.y *= f; v0.z *= f; v0.w *= f;
+        v1.x *= f; v1.y *= f; v1.z *= f; v1.w *= f;
+        v2.x *= f; v2.y *= f; v2.z *= f; v2.w *= f;
+        v3.x *= f; v3.y *= f; v3.z *= f; v3.w *= f;
+        m4[j] = v0; m4[j + step] = v1; m4[j + 2 * step] = v2; m4[j + 3 * step] = v3;
+      }
+      for (; j < n4; j += step) {
+        float4 v = m4[j];
+        v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+        m4[j] = v;
+      }
+      for (long long k = (n & ~3ll) + i0; k < n; k += step) m[k] *= f;
+    } else {
+      for (long long k = i0; k < n; k += step) m[k] *= f;
+    }
+  }
+  // remember the upstream gradient that arrived (a zero / non-finite one is not a usable assumption for the
+  // next forward: its gradients could not be rescaled)
+  __syncthreads();
+  if (threadIdx.x < n_states) {
+    unsigned* ticket = reinterpret_cast<unsigned*>(t.state[threadIdx.x] + 1);
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      const float g = __ldcg(t.got[threadIdx.x]);
+      if (g != 0.f && isfinite(g)) *t.state[threadIdx.x] = g;
+      *ticket = 0u;
+    }
+  }
 }
 
 }  // namespace
@@ -415,7 +482,7 @@ extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* con
                                          int n_levels, const float* limit_lo, const float* limit_hi,
                                          const float* radius_px, int batch, int max_gt, const float* gt_boxes,
                                          const int64_t* gt_labels, int mode, const float* grad_box,
-                                         const float* grad_cnt, int64_t* cls_t, float* cnt_t, float* reg_t,
+                                         const float* grad_cnt, int grad_mode, int64_t* cls_t, float* cnt_t, float* reg_t,
                                          float* box_loss, float* cnt_loss, float* num_pos, float* mean_out,
                                          float* reg_scale_grad, void* workspace, size_t workspace_bytes,
                                          void* stream) {
@@ -425,7 +492,7 @@ extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* con
     return B200DET_ERR_ARG;
   if (max_gt > 0 && (!gt_boxes || !gt_labels)) return B200DET_ERR_ARG;
   if (!aligned16(gt_boxes) || !aligned16(reg_t) || !aligned16(workspace)) return B200DET_ERR_ARG;
-  if (mode != 0 && mode != 1) return B200DET_ERR_UNSUPPORTED;
+  if ((mode != 0 && mode != 1) || (grad_mode != 0 && grad_mode != 1)) return B200DET_ERR_UNSUPPORTED;
   const bool has_cnt = cnt_grads != nullptr;
   if (has_cnt != (cnt_loss != nullptr)) return B200DET_ERR_ARG;
   int32_t level_hw[2 * B200DET_MAX_LEVELS], strides[B200DET_MAX_LEVELS];
@@ -483,7 +550,7 @@ extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* con
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
   e = cudaLaunchKernelEx(&cfg, tile_kernel, at, lm, has_cnt ? 1 : 0, max_gt, gt_boxes,
-                         reinterpret_cast<const long long*>(gt_labels), mode, grad_box, grad_cnt,
+                         reinterpret_cast<const long long*>(gt_labels), mode, grad_box, grad_cnt, grad_mode,
                          1.0f / (float)batch, (const float*)num_pos, reinterpret_cast<long long*>(cls_t), cnt_t, reg_t,
                          partial, no_pdl ? 0 : 1);
   if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
@@ -496,7 +563,7 @@ extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* con
   for (int l = 0; l <= B200DET_MAX_LEVELS; ++l) tl.tile_off[l] = at.tile_off[l];
   tl.n_levels = n_levels;
   e = cudaLaunchKernelEx(&cfg, finalize_losses_kernel, batch, n_tiles, tl, (const float*)partial,
-                         (const float*)num_pos, grad_box, 1.0f / (float)batch, box_loss, cnt_loss, mean_out,
+                         (const float*)num_pos, grad_box, grad_mode, 1.0f / (float)batch, box_loss, cnt_loss, mean_out,
                          reg_scale_grad, no_pdl ? 0 : 1);
   if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
   return check_launch();
@@ -513,5 +580,30 @@ extern "C" int b200det_scale_maps(float* const* maps, const int64_t* numel, cons
     t.numel[i] = numel[i];
   }
   scale_maps_kernel<<<dim3(74, n_maps), 256, 0, static_cast<cudaStream_t>(stream)>>>(t);
+  return check_launch();
+}
+
+extern "C" int b200det_rescale_maps(void* const* maps, const int64_t* numel, const int32_t* state_of, int dtype,
+                                    int n_maps, const float* const* got, float* const* state, int n_states,
+                                    void* stream) {
+  if (!maps || !numel || !state_of || !got || !state || n_maps <= 0 || n_maps > kMaxScaleMaps || n_states <= 0 ||
+      n_states > kMaxStates)
+    return B200DET_ERR_ARG;
+  if (dtype != B200DET_F32) return B200DET_ERR_UNSUPPORTED;
+  RescaleTable t = {};
+  for (int i = 0; i < n_maps; ++i) {
+    if (!maps[i] || numel[i] < 0 || state_of[i] < 0 || state_of[i] >= n_states) return B200DET_ERR_ARG;
+    t.map[i] = maps[i];
+    t.numel[i] = numel[i];
+    t.state_of[i] = state_of[i];
+  }
+  for (int s = 0; s < n_states; ++s) {
+    if (!got[s] || !state[s]) return B200DET_ERR_ARG;
+    for (int r = 0; r < s; ++r)
+      if (state[r] == state[s]) return B200DET_ERR_ARG;        // one ticket per state: list each state once
+    t.got[s] = got[s];
+    t.state[s] = state[s];
+  }
+  rescale_maps_kernel<<<kRescaleCtas, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, n_maps, n_states);
   return check_launch();
 }

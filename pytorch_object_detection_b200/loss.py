@@ -68,16 +68,41 @@ class _ClsLoss(torch.autograd.Function):
         return (None, None, *[g.to(c.dtype) for g, c in zip(grads, cls)])
 
 
-class _ClsLossStep(torch.autograd.Function):
-    """Batch-mean focal loss whose gradient is written by the forward kernel (one read of the logits).
+class _Upstream:
+    """The upstream gradient a loss output is ASSUMED to receive, kept on the device.
 
-    forward assumes the upstream gradient of the mean is 1 (``total_loss.backward()``); backward rescales
-    the stored maps only when it is not (a no-op launch otherwise).  One backward per forward."""
+    The step kernels write final gradients during the forward pass, so they must know dL/d(loss) in advance.
+    It starts at 1 (``total_loss.backward()``); every backward overwrites it with the value that actually
+    arrived (b200det_rescale_maps), and rescales the stored gradients only when the assumption was wrong.
+    Under ``torch.cuda.amp.GradScaler`` (train.py:127,180) the upstream gradient is the loss scale, which is
+    constant for thousands of steps: from the second step on the rescale pass never runs.  No host sync."""
+
+    def __init__(self):
+        self._value = {}
+
+    def on(self, device: torch.device) -> Tensor:
+        key = (device.type, device.index)
+        v = self._value.get(key)
+        if v is None:
+            v = torch.tensor([1.0, 0.0], dtype=torch.float32, device=device)     # {assumed, ticket}
+            if not torch.cuda.is_current_stream_capturing():
+                self._value[key] = v
+        return v
+
+
+def _as_scalar(g: Tensor) -> Tensor:
+    return g.detach().to(torch.float32).reshape(1).contiguous()
+
+
+class _ClsLossStep(torch.autograd.Function):
+    """Batch-mean focal loss whose gradient is written by the forward kernel (one read of the logits), for the
+    upstream gradient in ``up`` (see _Upstream); backward rescales only on a wrong assumption.  One backward
+    per forward."""
 
     @staticmethod
-    def forward(ctx, cls_t: Tensor, mask_src, num_pos, *cls: Tensor):
-        loss, mean, npos, grads = ops.cls_loss_step(cls, cls_t, mask_src=mask_src, num_pos=num_pos)
-        ctx.save_for_backward(*grads)
+    def forward(ctx, cls_t: Tensor, mask_src, num_pos, up: Tensor, *cls: Tensor):
+        loss, mean, npos, grads = ops.cls_loss_step(cls, cls_t, mask_src=mask_src, num_pos=num_pos, up_mean=up)
+        ctx.save_for_backward(up, *grads)
         ctx.dtypes = [t.dtype for t in cls]
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(loss, npos)
@@ -89,19 +114,19 @@ class _ClsLossStep(torch.autograd.Function):
             raise RuntimeError("the fused focal step supports a single backward per forward")
         ctx.consumed = True
         if g_mean is None:
-            return (None, None, None, *[None] * len(ctx.dtypes))
-        grads = list(ctx.saved_tensors)
-        f = g_mean.detach().to(torch.float32).reshape(())
-        ops.scale_maps_(grads, [f] * len(grads))
-        return (None, None, None, *[g.to(dt) for g, dt in zip(grads, ctx.dtypes)])
+            return (None, None, None, None, *[None] * len(ctx.dtypes))
+        up, *grads = ctx.saved_tensors
+        ops.rescale_maps_(grads, [_as_scalar(g_mean)] * len(grads), [up] * len(grads))
+        return (None, None, None, None, *[g.to(dt) for g, dt in zip(grads, ctx.dtypes)])
 
 
-def _cls_loss_mean(preds: List[Tensor], cls_t: Tensor, mask_src: Tensor | None, num_pos: Tensor | None) -> Tensor:
+def _cls_loss_mean(preds: List[Tensor], cls_t: Tensor, mask_src: Tensor | None, num_pos: Tensor | None,
+                   up: _Upstream) -> Tensor:
     """``compute_cls_loss(...).mean()`` (loss.py:210).  When a gradient will be asked for, the forward kernel
     writes it too (238 MB read once instead of twice at COCO batch 32); otherwise the forward kernel alone runs."""
     _check_points(preds, cls_t)                                    # loss.py:18
     if torch.is_grad_enabled() and any(t.requires_grad for t in preds):
-        return _ClsLossStep.apply(cls_t, mask_src, num_pos, *preds)[0]
+        return _ClsLossStep.apply(cls_t, mask_src, num_pos, up.on(preds[0].device), *preds)[0]
     if mask_src is None:
         raise ValueError("the forward-only focal loss needs the positive-mask source (cnt_t)")
     return _ClsLoss.apply(mask_src, cls_t, *preds).mean()
@@ -176,6 +201,7 @@ class FCOSLoss(nn.Module):
     def __init__(self, mode: str = "giou"):
         super().__init__()
         self.mode = mode
+        self._up_cls = _Upstream()
 
     def forward(self, x):
         pred, target = x
@@ -183,7 +209,7 @@ class FCOSLoss(nn.Module):
         cls_target, cnt_target, reg_target = target
         mask_pos = None                    # loss.py:205: cnt_target > -1; the kernels test cnt_target directly
         src = cnt_target
-        cls_loss = _cls_loss_mean(cls_logit, cls_target, src, None)
+        cls_loss = _cls_loss_mean(cls_logit, cls_target, src, None, self._up_cls)
         cnt_loss = compute_cnt_loss(cnt_logit, cnt_target, mask_pos, _mask_src=src).mean()
         reg_loss = compute_reg_loss(reg_logit, reg_target, mask_pos, self.mode, _mask_src=src).mean()
         total_loss = cls_loss + cnt_loss + reg_loss
@@ -193,19 +219,20 @@ class FCOSLoss(nn.Module):
 class _FusedTargetLoss(torch.autograd.Function):
     """Targets + box / centerness losses + their gradients from one kernel (csrc/train_fused.cu).
 
-    forward computes the gradients of the two batch means eagerly; backward only rescales them when the
-    upstream gradients differ from 1 (a no-op launch otherwise).  backward may run once per forward."""
+    forward computes the gradients of the two batch means eagerly for the upstream gradients assumed in
+    ``up_box`` / ``up_cnt`` (see _Upstream); backward only rescales them when an assumption was wrong (a no-op
+    launch otherwise).  backward may run once per forward."""
 
     @staticmethod
-    def forward(ctx, gt_boxes: Tensor, labels: Tensor, cfg, *maps: Tensor):
+    def forward(ctx, gt_boxes: Tensor, labels: Tensor, cfg, up_box: Tensor, up_cnt: Tensor, *maps: Tensor):
         strides, limit_range, mode, radius, n_reg, n_cnt = cfg
         reg, cnt, scales = maps[:n_reg], (maps[n_reg:n_reg + n_cnt] or None), (maps[n_reg + n_cnt:] or None)
         r = ops.assign_loss_fused(reg, cnt, strides, limit_range, gt_boxes, labels, mode, radius,
-                                  reg_exp_scales=scales)
+                                  reg_exp_scales=scales, up_box=up_box, up_cnt=up_cnt if cnt else None)
         ctx.n_reg, ctx.has_cnt = n_reg, cnt is not None
         ctx.dtypes = [t.dtype for t in maps]
         ctx.scale_shapes = [t.shape for t in scales] if scales else []
-        ctx.save_for_backward(*r["reg_grads"], *(r["cnt_grads"] or []),
+        ctx.save_for_backward(up_box, up_cnt, *r["reg_grads"], *(r["cnt_grads"] or []),
                               *([r["scale_grad"]] if scales else []))
         ctx.set_materialize_grads(False)
         mean = r["mean"]
@@ -218,26 +245,26 @@ class _FusedTargetLoss(torch.autograd.Function):
         if getattr(ctx, "consumed", False):
             raise RuntimeError("the fused target/loss step supports a single backward per forward")
         ctx.consumed = True
-        grads = list(ctx.saved_tensors)
+        up_box, up_cnt, *grads = ctx.saved_tensors
         n = ctx.n_reg
         scale_grad = grads.pop() if ctx.scale_shapes else None
-        todo, factors = [], []
+        todo, got, assumed = [], [], []
+        g_box = None if g_box is None else _as_scalar(g_box)
+        g_cnt = None if g_cnt is None else _as_scalar(g_cnt)
         for i, g in enumerate(grads):
-            up = g_box if i < n else g_cnt
-            if up is None:
+            arrived, up = (g_box, up_box) if i < n else (g_cnt, up_cnt)
+            if arrived is None:
                 grads[i] = None
             else:
-                todo.append(g)
-                factors.append(up.detach().to(torch.float32).reshape(()))
+                todo.append(g); got.append(arrived); assumed.append(up)
         if scale_grad is not None and g_box is not None:
-            todo.append(scale_grad)
-            factors.append(g_box.detach().to(torch.float32).reshape(()))
+            todo.append(scale_grad); got.append(g_box); assumed.append(up_box)
         if todo:
-            ops.scale_maps_(todo, factors)
+            ops.rescale_maps_(todo, got, assumed)
         out = [g if g is None else g.to(dt) for g, dt in zip(grads, ctx.dtypes)]
         if scale_grad is not None:                  # one gradient per ScaleExp.scale parameter
             out += [None if g_box is None else scale_grad[i].reshape(shp) for i, shp in enumerate(ctx.scale_shapes)]
-        return (None, None, None, *out)
+        return (None, None, None, None, None, *out)
 
 
 class FCOSTargetLoss(nn.Module):
@@ -265,6 +292,7 @@ class FCOSTargetLoss(nn.Module):
         self.sample_radio_ratio = float(sample_radio_ratio)
         self.reg_exp_scales = reg_exp_scales
         self.targets = None
+        self._up_cls, self._up_box, self._up_cnt = _Upstream(), _Upstream(), _Upstream()
 
     def box_cnt_losses(self, cnt_logits, reg_preds, gt_boxes: Tensor, labels: Tensor):
         """(reg_loss, cnt_loss) batch means + targets; ``cnt_logits`` may be None (box loss only)."""
@@ -274,7 +302,8 @@ class FCOSTargetLoss(nn.Module):
         maps = list(reg_preds[:n]) + (list(cnt_logits[:n]) if cnt_logits is not None else [])
         if self.reg_exp_scales is not None:
             maps += list(self.reg_exp_scales)[:n]
-        out = _FusedTargetLoss.apply(gt_boxes, labels, cfg, *maps)
+        dev = maps[0].device
+        out = _FusedTargetLoss.apply(gt_boxes, labels, cfg, self._up_box.on(dev), self._up_cnt.on(dev), *maps)
         self.targets = (out[2], out[3], out[4])
         self.per_image = {"reg": out[5], "num_pos": out[6], "cnt": out[7] if cnt_logits is not None else None}
         return out[0], (out[1] if cnt_logits is not None else None)
@@ -285,6 +314,6 @@ class FCOSTargetLoss(nn.Module):
         reg_loss, cnt_loss = self.box_cnt_losses(cnt_logits, reg_preds, gt_boxes, labels)
         cls_t, cnt_t, _ = self.targets
         n = min(len(self.strides), len(cls_logits))
-        cls_loss = _cls_loss_mean(list(cls_logits[:n]), cls_t, cnt_t, self.per_image["num_pos"])
+        cls_loss = _cls_loss_mean(list(cls_logits[:n]), cls_t, cnt_t, self.per_image["num_pos"], self._up_cls)
         total_loss = cls_loss + cnt_loss + reg_loss
         return cls_loss, cnt_loss, reg_loss, total_loss

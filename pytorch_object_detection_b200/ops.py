@@ -23,7 +23,7 @@ launch_count = 0          # kernels launched through this module (bench.py repor
 # kernels per C entry point (see csrc/*.cu)
 _LAUNCHES = {"postprocess": 4, "batched_nms": 3, "score_points": 1, "select_topk": 1, "clip_boxes": 1,
              "assign_targets": 1, "box_loss_fwd": 1, "box_loss_bwd": 1, "cnt_loss_fwd": 1, "cnt_loss_bwd": 1,
-             "cls_loss_fwd": 2, "cls_loss_bwd": 1, "cls_loss_step": 2, "count_pos": 1, "assign_loss_fused": 3, "scale_maps": 1,
+             "cls_loss_fwd": 2, "cls_loss_bwd": 1, "cls_loss_step": 2, "count_pos": 1, "assign_loss_fused": 3, "scale_maps": 1, "rescale_maps": 1,
              "pack_gt": 1, "collate_images": 1, "eval_ap": 2, "coco_boxes": 1}
 
 
@@ -431,12 +431,13 @@ def cls_loss_bwd(cls: Sequence[Tensor], cls_t: Tensor, grad_loss: Tensor, npos: 
 
 
 def cls_loss_step(cls: Sequence[Tensor], cls_t: Tensor, mask_src: Tensor | None = None,
-                  num_pos: Tensor | None = None, grad_loss: Tensor | None = None):
+                  num_pos: Tensor | None = None, grad_loss: Tensor | None = None, up_mean: Tensor | None = None):
     """compute_cls_loss forward AND backward from one read of the logits (b200det_cls_loss_step).
 
     ``num_pos`` [B] (from the fused assignment step) or ``mask_src`` (cnt_t, > -1 = positive) must be given.
     Returns (loss [B], mean [1], num_pos [B], grads) with grads = d(sum_b grad_loss[b] * loss[b]) / d(cls maps),
-    grad_loss defaulting to 1/B (the gradient of the batch mean)."""
+    grad_loss defaulting to 1/B (the gradient of the batch mean); ``up_mean`` (ONE fp32 CUDA value, exclusive
+    with grad_loss) is the upstream gradient of the batch mean, e.g. a GradScaler's loss scale: grad_loss[b] = up / B."""
     lib = _lib.load()
     lv, keep_alive, p_total, batch, n = _levels(cls, None, None, [1] * len(cls))
     dev = keep_alive[0].device
@@ -449,6 +450,9 @@ def cls_loss_step(cls: Sequence[Tensor], cls_t: Tensor, mask_src: Tensor | None 
     ready = num_pos is not None
     npos = _f32c(num_pos, "num_pos").reshape(batch) if ready else torch.empty((batch,), dtype=torch.float32, device=dev)
     gl = _f32c(grad_loss, "grad_loss").reshape(batch) if grad_loss is not None else None
+    if up_mean is not None:
+        assert grad_loss is None and up_mean.is_cuda and up_mean.dtype == torch.float32 and up_mean.numel() >= 1
+        gl = up_mean
     c = keep_alive[0].shape[1]
     ws_bytes = lib.b200det_cls_loss_workspace_bytes(batch, p_total, c)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -457,7 +461,8 @@ def cls_loss_step(cls: Sequence[Tensor], cls_t: Tensor, mask_src: Tensor | None 
     grads = [torch.empty_like(x) for x in keep_alive]
     ptr = lambda x: x.data_ptr() if x is not None else None
     with torch.cuda.device(dev):
-        rc = lib.b200det_cls_loss_step(lv, _grad_ptrs(grads), n, batch, c, t.data_ptr(), ptr(m), ptr(gl), int(ready),
+        rc = lib.b200det_cls_loss_step(lv, _grad_ptrs(grads), n, batch, c, t.data_ptr(), ptr(m), ptr(gl),
+                                       int(up_mean is not None), int(ready),
                                        ws.data_ptr(), ws_bytes, loss.data_ptr(), npos.data_ptr(), mean.data_ptr(),
                                        _stream(t))
     _lib.check(rc, "b200det_cls_loss_step")
@@ -489,7 +494,8 @@ def assign_loss_fused(reg: Sequence[Tensor], cnt: Sequence[Tensor] | None, strid
                       limit_range: Sequence[Sequence[float]], gt_boxes: Tensor, labels: Tensor, mode: int,
                       sample_radius: float = 1.5, grad_box: Tensor | None = None, grad_cnt: Tensor | None = None,
                       want_mean: bool = True, workspace: Tensor | None = None,
-                      reg_exp_scales: Sequence[Tensor] | None = None):
+                      reg_exp_scales: Sequence[Tensor] | None = None, up_box: Tensor | None = None,
+                      up_cnt: Tensor | None = None):
     """FCOSGenTargets.forward + compute_reg_loss (+ compute_cnt_loss) forward AND backward, one kernel.
 
     Returns a dict: cls_t [B,P,1] i64, cnt_t [B,P,1], reg_t [B,P,4] (bit-identical to assign_targets),
@@ -497,7 +503,8 @@ def assign_loss_fused(reg: Sequence[Tensor], cnt: Sequence[Tensor] | None, strid
     cnt_grads (lists shaped like the maps) = gradient of sum_b grad_*[b] * loss[b]; grad_* default to
     1/B, i.e. the gradient of the batch mean.  With ``reg_exp_scales`` (per level ONE fp32 CUDA value, the
     head's ScaleExp.scale) ``reg`` holds the raw regression outputs x, the distances are exp(x * scale),
-    reg_grads are gradients w.r.t. x and ``scale_grad`` [n_levels] w.r.t. the scales.  Concurrent calls on different streams of one device need
+    reg_grads are gradients w.r.t. x and ``scale_grad`` [n_levels] w.r.t. the scales.  ``up_box`` / ``up_cnt``
+    (ONE fp32 CUDA value each, instead of grad_box / grad_cnt) are upstream gradients of the two batch MEANS.  Concurrent calls on different streams of one device need
     their own ``workspace`` (b200det_assign_loss_workspace_bytes(B, P) bytes).
     """
     lib = _lib.load()
@@ -532,11 +539,17 @@ def assign_loss_fused(reg: Sequence[Tensor], cnt: Sequence[Tensor] | None, strid
     ws = workspace if workspace is not None else _fused_workspace(dev, batch, p_total)
     gb = _f32c(grad_box, "grad_box").reshape(batch) if grad_box is not None else None
     gc = _f32c(grad_cnt, "grad_cnt").reshape(batch) if grad_cnt is not None else None
+    grad_mode = 0
+    if up_box is not None or up_cnt is not None:
+        assert grad_box is None and grad_cnt is None and up_box is not None and (cnt is None or up_cnt is not None)
+        for u in (up_box, up_cnt):
+            assert u is None or (u.is_cuda and u.dtype == torch.float32 and u.numel() >= 1)
+        gb, gc, grad_mode = up_box, up_cnt, 1
     ptr = lambda t: t.data_ptr() if t is not None else None
     with torch.cuda.device(dev):
         rc = lib.b200det_assign_loss_fused(lv, _grad_ptrs(reg_grads), _grad_ptrs(cnt_grads) if cnt_grads else None, n,
                                            lo_arr, hi_arr, ra_arr, batch, m, gt.data_ptr(), lab.data_ptr(), int(mode),
-                                           ptr(gb), ptr(gc), cls_t.data_ptr(), cnt_t.data_ptr(), reg_t.data_ptr(),
+                                           ptr(gb), ptr(gc), grad_mode, cls_t.data_ptr(), cnt_t.data_ptr(), reg_t.data_ptr(),
                                            box_loss.data_ptr(), ptr(cnt_loss), num_pos.data_ptr(), ptr(mean),
                                            ptr(scale_grad), ptr(ws), ws.numel(), _stream(gt))
     _lib.check(rc, "b200det_assign_loss_fused")
@@ -561,6 +574,39 @@ def scale_maps_(maps: Sequence[Tensor], factors: Sequence[Tensor]) -> None:
         rc = lib.b200det_scale_maps(m_arr, n_arr, f_arr, n, _stream(maps[0]))
     _lib.check(rc, "b200det_scale_maps")
     _count("scale_maps")
+
+
+def rescale_maps_(maps: Sequence[Tensor], got: Sequence[Tensor], state: Sequence[Tensor]) -> None:
+    """maps[i] *= got[i] / state[i][0] where the two differ (nothing is touched where they are equal), then
+    state[i][0] <- got[i]: the backward of the steps whose forward wrote gradients for an assumed upstream
+    gradient (b200det_rescale_maps, one launch).  got: 1-element, state: 2-element {assumed, ticket} fp32 CUDA
+    tensors; maps that share a state object share its got."""
+    lib = _lib.load()
+    n = len(maps)
+    assert n == len(got) == len(state) and n > 0
+    states, gots, index = [], [], []
+    for t, g, a in zip(maps, got, state):
+        _need_cuda(t, "map")
+        assert t.dtype == torch.float32 and t.is_contiguous()
+        assert g.dtype == torch.float32 and g.numel() == 1 and g.is_cuda
+        assert a.dtype == torch.float32 and a.numel() == 2 and a.is_cuda and a.is_contiguous()
+        for k, s0 in enumerate(states):
+            if s0.data_ptr() == a.data_ptr():
+                index.append(k)
+                break
+        else:
+            index.append(len(states))
+            states.append(a)
+            gots.append(g)
+    m_arr = (C.c_void_p * n)(*[t.data_ptr() for t in maps])
+    n_arr = (C.c_int64 * n)(*[t.numel() for t in maps])
+    i_arr = (C.c_int32 * n)(*index)
+    g_arr = (C.c_void_p * len(states))(*[g.data_ptr() for g in gots])
+    s_arr = (C.c_void_p * len(states))(*[a.data_ptr() for a in states])
+    with torch.cuda.device(maps[0].device):
+        rc = lib.b200det_rescale_maps(m_arr, n_arr, i_arr, 0, n, g_arr, s_arr, len(states), _stream(maps[0]))
+    _lib.check(rc, "b200det_rescale_maps")
+    _count("rescale_maps")
 
 
 # --------------------------------------------------------------------------------------------

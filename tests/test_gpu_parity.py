@@ -526,6 +526,37 @@ def test_fused_target_loss_equals_unfused_kernels_full_size_and_upstream_scale()
         assert_close(to_np(t.grad), to_np(w) / 3.0, rel=REL_TOL, abs_=1e-10)
 
 
+def test_training_step_under_a_loss_scale_assumes_the_previous_upstream_gradient():
+    """train.py:175-181 runs the step under GradScaler: total_loss arrives in backward with the loss scale as
+    upstream gradient.  The step kernels write their gradients in the forward pass for an ASSUMED upstream
+    (start: 1), backward rescales on a wrong assumption and stores what arrived.  Every step must give the
+    reference's gradients times the scale — first step (wrong assumption), steady state, a scale change, a
+    zero upstream (grads 0, assumption kept) — against CPU autograd of the oracle."""
+    g, x, gt, labels, ranges, levels = train_case("train_voc_b2")
+    xc = cuda_levels(x)
+    flat = [t for part in xc for t in part]
+    for t in flat:
+        t.requires_grad_(True)
+    ref = [[t.clone().requires_grad_(True) for t in part] for part in x]
+    tgt = O.assign_targets(levels, gt, labels, W.STRIDES, ranges)
+    O.fcos_loss(ref, tgt[:3], "giou")[3].backward()
+    want = [t.grad.clone() for part in ref for t in part]
+    step = P.FCOSTargetLoss(W.STRIDES, ranges, "giou")
+    plain = P.FCOSLoss("giou")
+    for scale in (1024.0, 1024.0, 512.0, 0.0, 512.0):
+        for module, arg in ((step, [xc, gt.to(DEV), labels.to(DEV)]), (plain, None)):
+            for t in flat:
+                t.grad = None
+            if arg is None:
+                arg = [xc, P.FCOSGenTargets(W.STRIDES, ranges)([xc, gt.to(DEV), labels.to(DEV)])]
+            (module(arg)[3] * scale).backward()
+            for got, w in zip(flat, want):
+                assert_close(to_np(got.grad), to_np(w) * scale, rel=REL_TOL, abs_=1e-9 * max(scale, 1.0),
+                             what=f"{type(module).__name__} gradient at loss scale {scale}")
+    for up in (step._up_cls, step._up_box, step._up_cnt, plain._up_cls):
+        assert up.on(torch.device(DEV)).tolist() == [512.0, 0.0]  # the zero upstream was not adopted; ticket reset
+
+
 def test_fused_target_loss_edge_cases():
     """No GT at all, M = 0, one image, a slice-boundary-heavy tiny pyramid, dense crowd (300 GT)."""
     step = P.FCOSTargetLoss(W.STRIDES, W.FCOS_RANGES, "giou")
