@@ -176,6 +176,9 @@ int b200det_cls_loss_bwd(const b200det_level* levels, float* const* grads, int n
 
 /* The focal loss of a TRAINING STEP: loss and gradient from ONE read of the class logits
  * (compute_cls_loss forward, loss.py:6-26, and its autograd backward; the `.mean()` of loss.py:210).
+ *   cls_dtype (b200det_dtype): element type of levels[].cls AND of grads[] — fp32, or fp16 / bf16 as the
+ *     class convolution leaves them under torch.cuda.amp.autocast (train.py:175); arithmetic is fp32 either way
+ *     and a half gradient is rounded once (rn).  Use grad_mode 1 with a loss scale for fp16 gradients;
  *   grads[l] [B,C,h,w] receive d(sum_b grad_loss[b] * loss[b]) / d(cls level l);
  *   grad_loss: NULL for 1/B each (the gradient of the batch mean); grad_mode 0: [B] f32 device, dL/d(loss[b]);
  *     grad_mode 1: ONE f32 device value, the upstream gradient of the batch MEAN (a loss scale) -> /B each;
@@ -183,7 +186,7 @@ int b200det_cls_loss_bwd(const b200det_level* levels, float* const* grads, int n
  *     otherwise computed first from cnt_t (> -1 marks a positive) and written;
  *   loss [B] f32 = focal sum / num_pos; mean_out [1] f32 or NULL = batch mean, added in image order.
  * workspace: b200det_cls_loss_workspace_bytes(). */
-int b200det_cls_loss_step(const b200det_level* levels, float* const* grads, int n_levels, int batch,
+int b200det_cls_loss_step(const b200det_level* levels, void* const* grads, int cls_dtype, int n_levels, int batch,
                           int num_classes, const int64_t* cls_t, const float* cnt_t,
                           const float* grad_loss, int grad_mode, int num_pos_ready,
                           void* workspace, size_t workspace_bytes,

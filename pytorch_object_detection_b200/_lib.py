@@ -47,7 +47,8 @@ PROTOTYPES = {
     "b200det_cls_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "b200det_cls_loss_fwd": (C.c_int, [_LV, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P, _P, _P]),
     "b200det_cls_loss_bwd": (C.c_int, [_LV, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
-    "b200det_cls_loss_step": (C.c_int, [_LV, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, C.c_size_t,
+    "b200det_cls_loss_step": (C.c_int, [_LV, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P,
+                                        C.c_size_t,
                                         _P, _P, _P, _P]),
     "b200det_assign_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "b200det_assign_loss_fused": (C.c_int, [_LV, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int,

@@ -31,6 +31,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "assign_body.cuh"
 #include "loss_terms.cuh"
 
@@ -412,6 +415,63 @@ struct RescaleTable {
   float* state[kMaxStates];                  // {assumed upstream gradient, ticket (as bits of an unsigned)}
 };
 
+// map[i0 + k * step] *= f for one map, 128 bits per access where the map is 16-byte aligned
+template <typename T> struct RescaleVec;
+template <> struct RescaleVec<float> {
+  static constexpr int kPer = 4;
+  static __device__ __forceinline__ uint4 mul(uint4 v, const float f) {
+    float4 x = *reinterpret_cast<float4*>(&v);
+    x.x *= f; x.y *= f; x.z *= f; x.w *= f;
+    return *reinterpret_cast<uint4*>(&x);
+  }
+  static __device__ __forceinline__ void mul1(float* p, const float f) { *p *= f; }
+};
+template <> struct RescaleVec<__half> {
+  static constexpr int kPer = 8;
+  static __device__ __forceinline__ uint32_t pair(uint32_t w, const float f) {
+    const float2 x = __half22float2(*reinterpret_cast<__half2*>(&w));
+    const __half2 r = __floats2half2_rn(x.x * f, x.y * f);
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ uint4 mul(uint4 v, const float f) {
+    return make_uint4(pair(v.x, f), pair(v.y, f), pair(v.z, f), pair(v.w, f));
+  }
+  static __device__ __forceinline__ void mul1(__half* p, const float f) { *p = __float2half_rn(__half2float(*p) * f); }
+};
+template <> struct RescaleVec<__nv_bfloat16> {
+  static constexpr int kPer = 8;
+  static __device__ __forceinline__ uint32_t pair(uint32_t w, const float f) {
+    const float2 x = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w));
+    const __nv_bfloat162 r = __floats2bfloat162_rn(x.x * f, x.y * f);
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ uint4 mul(uint4 v, const float f) {
+    return make_uint4(pair(v.x, f), pair(v.y, f), pair(v.z, f), pair(v.w, f));
+  }
+  static __device__ __forceinline__ void mul1(__nv_bfloat16* p, const float f) {
+    *p = __float2bfloat16_rn(__bfloat162float(*p) * f);
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ void rescale_map(T* m, const long long n, const float f, const long long i0, const long long step) {
+  using V = RescaleVec<T>;
+  if ((reinterpret_cast<uintptr_t>(m) & 15u) == 0) {
+    uint4* m4 = reinterpret_cast<uint4*>(m);
+    const long long n4 = n / V::kPer;
+    long long j = i0;
+    for (; j + 3 * step < n4; j += 4 * step) {                 // four 128-bit loads in flight per thread
+      const uint4 v0 = m4[j], v1 = m4[j + step], v2 = m4[j + 2 * step], v3 = m4[j + 3 * step];
+      m4[j] = V::mul(v0, f); m4[j + step] = V::mul(v1, f); m4[j + 2 * step] = V::mul(v2, f); m4[j + 3 * step] = V::mul(v3, f);
+    }
+    for (; j < n4; j += step) m4[j] = V::mul(m4[j], f);
+    for (long long k = n4 * V::kPer + i0; k < n; k += step) V::mul1(m + k, f);
+  } else {
+    for (long long k = i0; k < n; k += step) V::mul1(m + k, f);
+  }
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) rescale_maps_kernel(const RescaleTable t, const int n_maps, const int n_states) {
   __shared__ float s_f[kMaxStates];
   if (threadIdx.x < n_states) {
@@ -423,30 +483,7 @@ __global__ void __launch_bounds__(256) rescale_maps_kernel(const RescaleTable t,
   const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
   for (int i = 0; i < n_maps; ++i) {
     const float f = s_f[t.state_of[i]];
-    if (f == 1.0f) continue;
-    float* m = static_cast<float*>(t.map[i]);
-    const long long n = t.numel[i];
-    if ((reinterpret_cast<uintptr_t>(m) & 15u) == 0) {
-      float4* m4 = reinterpret_cast<float4*>(m);
-      const long long n4 = n / 4;
-      long long j = i0;
-      for (; j + 3 * step < n4; j += 4 * step) {                 // four 128-bit loads in flight per thread
-        float4 v0 = m4[j], v1 = m4[j + step], v2 = m4[j + 2 * step], v3 = m4[j + 3 * step];
-        v0.x *= f; v0.y *= f; v0.z *= f; v0.w *= f;
-        v1.x *= f; v1.y *= f; v1.z *= f; v1.w *= f;
-        v2.x *= f; v2.y *= f; v2.z *= f; v2.w *= f;
-        v3.x *= f; v3.y *= f; v3.z *= f; v3.w *= f;
-        m4[j] = v0; m4[j + step] = v1; m4[j + 2 * step] = v2; m4[j + 3 * step] = v3;
-      }
-      for (; j < n4; j += step) {
-        float4 v = m4[j];
-        v.x *= f; v.y *= f; v.z *= f; v.w *= f;
-        m4[j] = v;
-      }
-      for (long long k = (n & ~3ll) + i0; k < n; k += step) m[k] *= f;
-    } else {
-      for (long long k = i0; k < n; k += step) m[k] *= f;
-    }
+    if (f != 1.0f) rescale_map(static_cast<T*>(t.map[i]), t.numel[i], f, i0, step);
   }
   // remember the upstream gradient that arrived (a zero / non-finite one is not a usable assumption for the
   // next forward: its gradients could not be rescaled)
@@ -589,7 +626,7 @@ extern "C" int b200det_rescale_maps(void* const* maps, const int64_t* numel, con
   if (!maps || !numel || !state_of || !got || !state || n_maps <= 0 || n_maps > kMaxScaleMaps || n_states <= 0 ||
       n_states > kMaxStates)
     return B200DET_ERR_ARG;
-  if (dtype != B200DET_F32) return B200DET_ERR_UNSUPPORTED;
+  if (dtype != B200DET_F32 && dtype != B200DET_F16 && dtype != B200DET_BF16) return B200DET_ERR_UNSUPPORTED;
   RescaleTable t = {};
   for (int i = 0; i < n_maps; ++i) {
     if (!maps[i] || numel[i] < 0 || state_of[i] < 0 || state_of[i] >= n_states) return B200DET_ERR_ARG;
@@ -604,6 +641,9 @@ extern "C" int b200det_rescale_maps(void* const* maps, const int64_t* numel, con
     t.got[s] = got[s];
     t.state[s] = state[s];
   }
-  rescale_maps_kernel<<<kRescaleCtas, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, n_maps, n_states);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == B200DET_F32) rescale_maps_kernel<float><<<kRescaleCtas, 256, 0, st>>>(t, n_maps, n_states);
+  else if (dtype == B200DET_F16) rescale_maps_kernel<__half><<<kRescaleCtas, 256, 0, st>>>(t, n_maps, n_states);
+  else rescale_maps_kernel<__nv_bfloat16><<<kRescaleCtas, 256, 0, st>>>(t, n_maps, n_states);
   return check_launch();
 }

@@ -79,6 +79,7 @@ class _Upstream:
 
     def __init__(self):
         self._value = {}
+        self.observed = False        # a backward has stored the upstream gradient that really arrives
 
     def on(self, device: torch.device) -> Tensor:
         key = (device.type, device.index)
@@ -96,13 +97,15 @@ def _as_scalar(g: Tensor) -> Tensor:
 
 class _ClsLossStep(torch.autograd.Function):
     """Batch-mean focal loss whose gradient is written by the forward kernel (one read of the logits), for the
-    upstream gradient in ``up`` (see _Upstream); backward rescales only on a wrong assumption.  One backward
-    per forward."""
+    upstream gradient assumed in ``up`` (see _Upstream); backward rescales only on a wrong assumption.  fp16 /
+    bf16 logits are read as they are and the gradient is written in their type.  One backward per forward."""
 
     @staticmethod
-    def forward(ctx, cls_t: Tensor, mask_src, num_pos, up: Tensor, *cls: Tensor):
-        loss, mean, npos, grads = ops.cls_loss_step(cls, cls_t, mask_src=mask_src, num_pos=num_pos, up_mean=up)
-        ctx.save_for_backward(up, *grads)
+    def forward(ctx, cls_t: Tensor, mask_src, num_pos, up: _Upstream, *cls: Tensor):
+        state = up.on(cls[0].device)
+        loss, mean, npos, grads = ops.cls_loss_step(cls, cls_t, mask_src=mask_src, num_pos=num_pos, up_mean=state)
+        ctx.save_for_backward(state, *grads)
+        ctx.up = up
         ctx.dtypes = [t.dtype for t in cls]
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(loss, npos)
@@ -115,9 +118,29 @@ class _ClsLossStep(torch.autograd.Function):
         ctx.consumed = True
         if g_mean is None:
             return (None, None, None, None, *[None] * len(ctx.dtypes))
-        up, *grads = ctx.saved_tensors
-        ops.rescale_maps_(grads, [_as_scalar(g_mean)] * len(grads), [up] * len(grads))
+        state, *grads = ctx.saved_tensors
+        ops.rescale_maps_(grads, [_as_scalar(g_mean)] * len(grads), [state] * len(grads))
+        ctx.up.observed = True
         return (None, None, None, None, *[g.to(dt) for g, dt in zip(grads, ctx.dtypes)])
+
+
+class _TapUpstream(torch.autograd.Function):
+    """Identity whose backward stores the gradient that arrives into an _Upstream (first step of half-precision
+    logits: fp16 gradients written for a wrongly assumed loss scale would have underflowed)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, up: _Upstream):
+        ctx.up = up
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        if g is not None:
+            word = ctx.up.on(g.device)[:1]
+            arrived = _as_scalar(g)
+            word.copy_(torch.where((arrived != 0) & torch.isfinite(arrived), arrived, word))
+            ctx.up.observed = True
+        return g, None
 
 
 def _cls_loss_mean(preds: List[Tensor], cls_t: Tensor, mask_src: Tensor | None, num_pos: Tensor | None,
@@ -126,7 +149,12 @@ def _cls_loss_mean(preds: List[Tensor], cls_t: Tensor, mask_src: Tensor | None, 
     writes it too (238 MB read once instead of twice at COCO batch 32); otherwise the forward kernel alone runs."""
     _check_points(preds, cls_t)                                    # loss.py:18
     if torch.is_grad_enabled() and any(t.requires_grad for t in preds):
-        return _ClsLossStep.apply(cls_t, mask_src, num_pos, up.on(preds[0].device), *preds)[0]
+        half = preds[0].dtype in (torch.float16, torch.bfloat16)
+        if not half or up.observed:
+            return _ClsLossStep.apply(cls_t, mask_src, num_pos, up, *preds)[0]
+        # half-precision logits, first step: the loss scale is not known yet -> forward and backward kernels
+        if mask_src is not None:
+            return _TapUpstream.apply(_ClsLoss.apply(mask_src, cls_t, *preds).mean(), up)
     if mask_src is None:
         raise ValueError("the forward-only focal loss needs the positive-mask source (cnt_t)")
     return _ClsLoss.apply(mask_src, cls_t, *preds).mean()

@@ -67,9 +67,13 @@ def _scale_ptrs(reg_exp_scales, n: int, keep: List[Tensor]):
     return out
 
 
+_DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}       # b200det_dtype
+
+
 def _levels(cls: Sequence[Tensor] | None, cnt: Sequence[Tensor] | None, reg: Sequence[Tensor] | None,
-            strides: Sequence[int], reg_exp_scales=None):
-    """zip()-truncated level table.  Returns (ctypes array, kept tensors, P, batch, n_levels)."""
+            strides: Sequence[int], reg_exp_scales=None, keep_half_cls: bool = False):
+    """zip()-truncated level table.  Returns (ctypes array, kept tensors, P, batch, n_levels).  With
+    ``keep_half_cls`` fp16 / bf16 class maps are passed as they are (entry points that take a cls_dtype)."""
     lists = [l for l in (cls, cnt, reg) if l is not None]
     n = min([len(strides)] + [len(l) for l in lists])
     if n == 0:
@@ -85,7 +89,11 @@ def _levels(cls: Sequence[Tensor] | None, cnt: Sequence[Tensor] | None, reg: Seq
             if lst is None:
                 ptrs.append(0)
                 continue
-            t = _f32c(lst[i], "level map")
+            if keep_half_cls and ch is None and lst[i].dtype in (torch.float16, torch.bfloat16):
+                _need_cuda(lst[i], "level map")
+                t = lst[i] if lst[i].is_contiguous() else lst[i].contiguous()
+            else:
+                t = _f32c(lst[i], "level map")
             if t.dim() != 4 or (ch is not None and t.shape[1] != ch):
                 raise _lib.B200DetError(f"level {i}: expected [B,{ch or 'C'},h,w], got {tuple(t.shape)}")
             if hw is None:
@@ -435,12 +443,15 @@ def cls_loss_step(cls: Sequence[Tensor], cls_t: Tensor, mask_src: Tensor | None 
     """compute_cls_loss forward AND backward from one read of the logits (b200det_cls_loss_step).
 
     ``num_pos`` [B] (from the fused assignment step) or ``mask_src`` (cnt_t, > -1 = positive) must be given.
+    fp16 / bf16 class maps are read as they are and their gradients come back in the same type (fp32 arithmetic).
     Returns (loss [B], mean [1], num_pos [B], grads) with grads = d(sum_b grad_loss[b] * loss[b]) / d(cls maps),
     grad_loss defaulting to 1/B (the gradient of the batch mean); ``up_mean`` (ONE fp32 CUDA value, exclusive
     with grad_loss) is the upstream gradient of the batch mean, e.g. a GradScaler's loss scale: grad_loss[b] = up / B."""
     lib = _lib.load()
-    lv, keep_alive, p_total, batch, n = _levels(cls, None, None, [1] * len(cls))
+    half = all(x.dtype == cls[0].dtype for x in cls) and cls[0].dtype in (torch.float16, torch.bfloat16)
+    lv, keep_alive, p_total, batch, n = _levels(cls, None, None, [1] * len(cls), keep_half_cls=half)
     dev = keep_alive[0].device
+    dtype_code = _DTYPE_CODE[keep_alive[0].dtype]
     _need_cuda(cls_t, "cls target")
     t = cls_t.to(torch.int64).reshape(batch, -1).contiguous()
     assert t.shape[1] == p_total
@@ -461,7 +472,7 @@ def cls_loss_step(cls: Sequence[Tensor], cls_t: Tensor, mask_src: Tensor | None 
     grads = [torch.empty_like(x) for x in keep_alive]
     ptr = lambda x: x.data_ptr() if x is not None else None
     with torch.cuda.device(dev):
-        rc = lib.b200det_cls_loss_step(lv, _grad_ptrs(grads), n, batch, c, t.data_ptr(), ptr(m), ptr(gl),
+        rc = lib.b200det_cls_loss_step(lv, _grad_ptrs(grads), dtype_code, n, batch, c, t.data_ptr(), ptr(m), ptr(gl),
                                        int(up_mean is not None), int(ready),
                                        ws.data_ptr(), ws_bytes, loss.data_ptr(), npos.data_ptr(), mean.data_ptr(),
                                        _stream(t))
@@ -587,7 +598,7 @@ def rescale_maps_(maps: Sequence[Tensor], got: Sequence[Tensor], state: Sequence
     states, gots, index = [], [], []
     for t, g, a in zip(maps, got, state):
         _need_cuda(t, "map")
-        assert t.dtype == torch.float32 and t.is_contiguous()
+        assert t.dtype == maps[0].dtype and t.dtype in _DTYPE_CODE and t.is_contiguous()
         assert g.dtype == torch.float32 and g.numel() == 1 and g.is_cuda
         assert a.dtype == torch.float32 and a.numel() == 2 and a.is_cuda and a.is_contiguous()
         for k, s0 in enumerate(states):
@@ -604,7 +615,7 @@ def rescale_maps_(maps: Sequence[Tensor], got: Sequence[Tensor], state: Sequence
     g_arr = (C.c_void_p * len(states))(*[g.data_ptr() for g in gots])
     s_arr = (C.c_void_p * len(states))(*[a.data_ptr() for a in states])
     with torch.cuda.device(maps[0].device):
-        rc = lib.b200det_rescale_maps(m_arr, n_arr, i_arr, 0, n, g_arr, s_arr, len(states), _stream(maps[0]))
+        rc = lib.b200det_rescale_maps(m_arr, n_arr, i_arr, _DTYPE_CODE[maps[0].dtype], n, g_arr, s_arr, len(states), _stream(maps[0]))
     _lib.check(rc, "b200det_rescale_maps")
     _count("rescale_maps")
 

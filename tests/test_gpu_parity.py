@@ -557,6 +557,72 @@ def test_training_step_under_a_loss_scale_assumes_the_previous_upstream_gradient
         assert up.on(torch.device(DEV)).tolist() == [512.0, 0.0]  # the zero upstream was not adopted; ticket reset
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_focal_step_reads_half_logits_and_writes_half_gradients(dtype):
+    """Under autocast (train.py:175) the class logits are fp16 conv outputs.  b200det_cls_loss_step reads them as
+    they are and writes the gradient in their type; the arithmetic is the fp32 kernel's: the loss must be
+    BIT-IDENTICAL to the fp32 kernel on the up-cast logits and the gradient identical to its gradient rounded
+    once.  Levels cover the staged path (hw % 8 == 0), the 4-element path (26 x 42, 7 x 12) and the scalar path."""
+    gen = torch.Generator().manual_seed(23)
+    B, C = 2, 21
+    levels = [(40, 52), (26, 42), (13, 21), (7, 12), (1, 3)]
+    P_total = sum(h * w for h, w in levels)
+    cls = [((torch.randn(B, C, h, w, generator=gen) * 2.0 - 3.0).to(dtype)).to(DEV) for h, w in levels]
+    cls_t = torch.zeros(B, P_total, 1, dtype=torch.int64)
+    pos = torch.rand(B, P_total, generator=gen) < 0.03
+    cls_t[pos] = torch.randint(1, C + 1, (int(pos.sum()), 1), generator=gen)
+    cnt_t = torch.where(pos, 0.5, -1.0).reshape(B, P_total, 1).to(DEV)
+    state = torch.tensor([1024.0, 0.0], device=DEV)                      # a loss scale: fp16 gradients need one
+    loss_h, mean_h, npos_h, grads_h = ops.cls_loss_step(cls, cls_t.to(DEV), mask_src=cnt_t, up_mean=state)
+    loss_f, mean_f, npos_f, grads_f = ops.cls_loss_step([t.float() for t in cls], cls_t.to(DEV), mask_src=cnt_t,
+                                                        up_mean=state)
+    assert torch.equal(loss_h, loss_f) and torch.equal(mean_h, mean_f) and torch.equal(npos_h, npos_f)
+    for gh, gf in zip(grads_h, grads_f):
+        assert gh.dtype == dtype and torch.equal(gh, gf.to(dtype))
+    # against the reference formula on the CPU (fp32 on the up-cast logits)
+    ref_in = [t.float().cpu().requires_grad_(True) for t in cls]
+    want = O.cls_loss(ref_in, cls_t, pos)
+    (want.mean() * 1024.0).backward()
+    assert_close(to_np(loss_h), to_np(want), rel=REL_TOL, what="focal loss of half logits")
+    half_ulp = 2.0 ** -11 if dtype == torch.float16 else 2.0 ** -8
+    for gh, r in zip(grads_h, ref_in):
+        assert_close(to_np(gh.float()), to_np(r.grad), rel=2.0 * half_ulp, abs_=1e-7, what="half focal gradient")
+    # a wrong assumption is repaired in the half maps themselves (x 0.5: exact in fp16 above the subnormals)
+    got = torch.tensor([512.0], device=DEV)
+    ops.rescale_maps_(grads_h, [got] * len(grads_h), [state] * len(grads_h))
+    assert state.tolist() == [512.0, 0.0]
+    for gh, r in zip(grads_h, ref_in):
+        assert_close(to_np(gh.float()), to_np(r.grad) * 0.5, rel=3.0 * half_ulp, abs_=1e-7, what="rescaled half gradient")
+
+
+def test_training_step_with_autocast_style_half_logits():
+    """FCOSTargetLoss on fp16 cls / cnt maps (what autocast hands over) under a loss scale, three steps: the first
+    takes the two-kernel focal path and taps the upstream gradient, the next ones the step kernel on fp16 maps."""
+    g, x, gt, labels, ranges, levels = train_case("train_voc_b2")
+    cls32, cnt32, reg32 = x
+    xh = ([t.half().to(DEV).requires_grad_(True) for t in cls32], [t.half().to(DEV).requires_grad_(True) for t in cnt32],
+          [t.to(DEV).requires_grad_(True) for t in reg32])
+    ref = ([t.half().float().requires_grad_(True) for t in cls32], [t.half().float().requires_grad_(True) for t in cnt32],
+           [t.clone().requires_grad_(True) for t in reg32])
+    tgt = O.assign_targets(levels, gt, labels, W.STRIDES, ranges)
+    want_losses = O.fcos_loss(ref, tgt[:3], "giou")
+    want_losses[3].backward()
+    step = P.FCOSTargetLoss(W.STRIDES, ranges, "giou")
+    for it, scale in enumerate((4096.0, 4096.0, 2048.0)):
+        for part in xh:
+            for t in part:
+                t.grad = None
+        losses = step([xh, gt.to(DEV), labels.to(DEV)])
+        assert step._up_cls.observed == (it > 0)
+        assert_close([float(v) for v in losses], [float(v) for v in want_losses], rel=REL_TOL, what="losses, half logits")
+        (losses[3] * scale).backward()
+        for part, rpart in zip(xh, ref):
+            for t, r in zip(part, rpart):
+                assert t.grad.dtype == t.dtype
+                assert_close(to_np(t.grad.float()), to_np(r.grad) * scale, rel=2e-3, abs_=1e-6 * scale,
+                             what=f"step {it} gradient ({t.dtype})")
+
+
 def test_fused_target_loss_edge_cases():
     """No GT at all, M = 0, one image, a slice-boundary-heavy tiny pyramid, dense crowd (300 GT)."""
     step = P.FCOSTargetLoss(W.STRIDES, W.FCOS_RANGES, "giou")
