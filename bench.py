@@ -461,6 +461,13 @@ def main():
             us_full_two = timed_graph(train_step_full_two_focal_kernels, args.steps)
             us_focal = timed_graph(lambda i: ops.cls_loss_step(clss[i % 2], fused.targets[0],
                                                                num_pos=fused.per_image["num_pos"]), args.steps)
+            # the autocast case (train.py:175): fp16 class logits read as they are, fp16 gradients written
+            cls_h = [[t.detach().half() for t in clss[i]] for i in range(2)]
+            scale_state = torch.tensor([65536.0, 0.0], device=dev)
+            us_focal_h = timed_graph(lambda i: ops.cls_loss_step(cls_h[i % 2], fused.targets[0],
+                                                                 num_pos=fused.per_image["num_pos"],
+                                                                 up_mean=scale_state), args.steps)
+            del cls_h
             # assign alone, for its own roofline: 28 bytes written per point
             us_assign = timed_graph(
                 lambda i: ops.assign_targets(W.COCO_LEVELS, W.STRIDES, W.HISFCOS_RANGES, gt, labels), args.steps)
@@ -477,7 +484,8 @@ def main():
                                "us_per_batch": us_full, "us_with_two_focal_kernels": us_full_two,
                                "focal_step_kernel_us": us_focal, "focal_bytes": 2 * TRAIN_BATCH * P * NCLS * 4,
                                "focal_gbs": 2 * TRAIN_BATCH * P * NCLS * 4 / (us_focal * 1e-6) / 1e9,
-                               "focal_frac_of_peak": 2 * TRAIN_BATCH * P * NCLS * 4 / (us_focal * 1e-6) / 1e9 / peak},
+                               "focal_frac_of_peak": 2 * TRAIN_BATCH * P * NCLS * 4 / (us_focal * 1e-6) / 1e9 / peak,
+                               "focal_step_kernel_fp16_logits_us": us_focal_h},
                  "assign_us": us_assign, "assign_bytes": assign_bytes,
                  "assign_gbs": assign_bytes / (us_assign * 1e-6) / 1e9,
                  "assign_frac_of_peak": assign_bytes / (us_assign * 1e-6) / 1e9 / peak}

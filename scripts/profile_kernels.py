@@ -46,6 +46,9 @@ score, cls0 = ops.score_points(sets[0][0], sets[0][1], W.STRIDES)
 cand = ops.select_topk(sets[0][2], W.STRIDES, score, cls0, 0.05, 1000)
 npos = ops.box_loss_fwd(tsets[0][2], tgt[1], tgt[2], 1)[1]
 
+tsets_h = [[t.half() for t in ts[0]] for ts in tsets]              # autocast: fp16 class logits
+scale_state = torch.tensor([65536.0, 0.0], device=dev)             # {assumed loss scale, ticket}
+
 crowd = [W.crowd_candidates(5000, 80, seed=400 + i) for i in range(8)]
 cb = torch.stack([c[0] for c in crowd]).to(dev)
 cs = torch.stack([c[1] for c in crowd]).to(dev)
@@ -64,6 +67,7 @@ cases = {
     "cls_loss_fwd": lambda i: ops.cls_loss_fwd(tsets[i % 2][0], tgt[1], tgt[0]),
     "cls_loss_bwd": lambda i: ops.cls_loss_bwd(tsets[i % 2][0], tgt[0], gl, npos),
     "cls_loss_step": lambda i: ops.cls_loss_step(tsets[i % 2][0], tgt[0], num_pos=npos),
+    "cls_loss_step_f16": lambda i: ops.cls_loss_step(tsets_h[i % 2], tgt[0], num_pos=npos, up_mean=scale_state),
 }
 only = [s for s in args.only.split(",") if s]
 for name, fn in cases.items():
