@@ -133,8 +133,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sets", type=int, default=4, help="input sets rotated through (each 127 MB; L2 is 126 MB)")
-    ap.add_argument("--streams", type=int, default=3, help="batches in flight (CUDA streams) in the timed loop")
+    ap.add_argument("--sets", type=int, default=8, help="input sets rotated through (each 127 MB; L2 is 126 MB)")
+    ap.add_argument("--streams", type=int, default=8, help="batches in flight (CUDA streams) in the timed loop; "
+                    "measured on B200: 3 -> 26.0, 4 -> 22.6, 6 -> 21.5, 8 -> 21.0 us per batch-16 step (K1 alone: 20.7)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
