@@ -226,15 +226,40 @@ def main():
                     head.detect(hs, clip_hw=W.COCO_HW, out_packed=out_big[s_i])
             for st in side:
                 cs.wait_stream(st)                        # join
-        full = torch.empty((world, count * pk_bytes), dtype=torch.uint8, device=dev) if world > 1 else None
+        full = torch.empty((world, count * pk_bytes), dtype=torch.uint8, device=dev) if world > 1 and peer is None else None
         return g, out_big, full
+
+    # The gather: peer-memory pushes on the copy engines + a device-side barrier (sharding.PeerGather); NCCL
+    # all_gather when symmetric memory is not available (B200DET_BENCH_GATHER=nccl forces it).  The detections
+    # are gathered to rank 0, where an evaluation collects them (Test_coco.py:144-168 writes one result file);
+    # B200DET_BENCH_GATHER=peer_all gives every rank every detection instead (8 GPUs: 24.2 us per step).
+    peer = None
+    gather_kind = "none"
+    if dist is not None:
+        gather_kind = "NCCL all_gather"
+        gather_mode = os.environ.get("B200DET_BENCH_GATHER", "peer_root")      # peer_root | peer_all | nccl
+        gather_root = 0 if gather_mode == "peer_root" else None
+        if gather_mode.startswith("peer"):
+            try:
+                from pytorch_object_detection_b200.sharding import PeerGather
+                peer = PeerGather(args.sets * pk_bytes, 4, dev)
+                gather_kind = ("gather to rank 0" if gather_root == 0 else "all-gather") + \
+                    " by peer-memory pushes (copy engines) + device barrier"
+            except Exception as e:                          # noqa: BLE001
+                print(f"[bench] rank {rank}: symmetric memory unavailable ({type(e).__name__}: {e}); NCCL all_gather",
+                      file=sys.stderr)
+                peer = None
+        flags = torch.tensor([1.0 if peer is not None else 0.0], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)        # every rank must take the same path
+        if float(flags[0]) == 0.0:
+            peer, gather_kind = None, "NCCL all_gather"
 
     def timed_rounds(n_streams):
         n_buf = 4                                                  # output buffers (graphs) in rotation
-        rounds = [capture_round(n_streams) for _ in range(n_buf)]
+        rounds = [list(capture_round(n_streams)) for _ in range(n_buf)]
         n_rounds, tail = divmod(args.steps, args.sets)             # EXACTLY args.steps steps are timed
         if tail:
-            rounds.append(capture_round(n_streams, tail))
+            rounds.append(list(capture_round(n_streams, tail)))
         pending = [None] * (n_buf + 1)
         # rounds A and B are replayed on two different streams so that the tail of one round overlaps the
         # head of the next (a replay of A still waits for the previous replay of A: same stream)
@@ -255,7 +280,12 @@ def main():
                 # the collective is issued from its own stream, which waits for this round only
                 with torch.cuda.stream(gather_stream):
                     gather_stream.wait_event(done[q])
-                    dist.all_gather_into_tensor(full, out_big.reshape(-1))
+                    if peer is not None and out_big.numel() == peer.nbytes:
+                        peer.gather(q % peer.slots, out_big.reshape(-1), root=gather_root)
+                    else:
+                        if full is None:                    # the shorter tail round
+                            full = rounds[q][2] = torch.empty((world, out_big.numel()), dtype=torch.uint8, device=dev)
+                        dist.all_gather_into_tensor(full, out_big.reshape(-1))
                     pending[q] = torch.cuda.Event()
                     pending[q].record()
 
@@ -534,7 +564,7 @@ def main():
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH,
                        "l2": f"{args.sets} input sets of {in_bytes / 1e6:.0f} MB rotated (> 126 MB L2)",
                        "in_flight": f"{n_streams} batches on {n_streams} CUDA streams inside one CUDA graph of {args.sets} steps",
-                       "collective": f"one all_gather of the packed detections per {args.sets} steps, overlapped" if world > 1 else "none"},
+                       "collective": f"one gather of the packed detections per {args.sets} steps, overlapped: {gather_kind}" if world > 1 else "none"},
             "single_stream": {"value": world * BATCH / (ms_single * 1e-3), "unit": "img/s", "ms_per_step": ms_single},
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "steps": e2e_steps, "api": "FCOSHead.detect(clip_hw=...) on pinned host inputs"},

@@ -79,6 +79,50 @@ def gather_packed(packed: Tensor, out: Tensor | None = None, group=None) -> Tens
     return out
 
 
+class PeerGather:
+    """The final detection gather without a collective kernel: every rank PUSHES its packed buffer into its
+    slot of each peer's receive buffer through NVLink peer memory (``cudaMemcpyAsync`` onto symmetric memory,
+    i.e. the copy engines — no SM is taken from the HBM-bound kernels that keep running), then one small
+    device-side barrier on the signal pads tells every rank that all slots have landed.
+
+    Measured against NCCL ``all_gather`` in ``bench.py`` (the NCCL kernel's duration is exposed: its CTAs wait
+    for SM resources behind the saturating post-process kernels).  ``slots`` receive buffers rotate so that a
+    consumer may read slot q while later gathers fill the others; consume a slot in stream order before
+    ``gather`` is called ``slots`` more times.  Needs P2P-capable GPUs of one node (NVLink / NVSwitch) and a
+    ``torch.distributed`` process group with one rank per GPU; raises if symmetric memory is unavailable
+    (callers fall back to ``gather_packed``).  All ranks must call ``gather`` in the same order.
+    """
+
+    def __init__(self, nbytes: int, slots: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.nbytes, self.slots = int(nbytes), int(slots)
+        shape = (self.slots, self.world, self.nbytes)
+        self.recv = symm_mem.empty(shape, dtype=torch.uint8, device=device)
+        self.handle = symm_mem.rendezvous(self.recv, self.group)
+        self.peers = [self.handle.get_buffer(p, shape, torch.uint8) for p in range(self.world)]
+        self.handle.barrier(channel=0)
+
+    def gather(self, slot: int, packed: Tensor, root: int | None = None) -> Tensor:
+        """Push ``packed`` (uint8 [nbytes], on this device) into ``slot`` of every rank (``root=None``, an
+        all-gather) or of rank ``root`` only (a gather: the other ranks send one buffer and receive nothing).
+        Returns this rank's ``[world, nbytes]`` view of the slot, complete — on the receiving ranks — once the
+        current stream reaches this point."""
+        if packed.numel() != self.nbytes or packed.dtype != torch.uint8:
+            raise ValueError("PeerGather.gather: packed must be uint8 of the size given at construction")
+        if root is None:
+            for k in range(self.world):                    # start with the neighbour: no two ranks hit one peer first
+                p = (self.rank + 1 + k) % self.world
+                self.peers[p][slot, self.rank].copy_(packed, non_blocking=True)
+        else:
+            self.peers[root][slot, self.rank].copy_(packed, non_blocking=True)
+        self.handle.barrier(channel=0)                     # also keeps the ranks within `slots` gathers of each other
+        return self.recv[slot]
+
+
 def packed_of(scores: Tensor) -> Tensor:
     """The packed uint8 buffer behind the outputs of ``ops.postprocess`` / ``FCOSHead.detect``."""
     st = scores.untyped_storage()
