@@ -15,8 +15,9 @@ GPU).  Prints ONE JSON line:
   train     BASELINE config 3 (target assign + GIoU fwd/bwd, B=32, M<=100): us/batch + roofline
 With --impl reference the oracle port (the reference is pure Python and does not travel to the
 GPU box; the port is pinned against it by tests/golden) is timed on the host cores instead.
-Multi-GPU (torchrun): batch sharded by rank (weak scaling, 16 images per GPU), one final NCCL
-all_gather of the padded detections per step; time = max over ranks.
+Multi-GPU (torchrun): batch sharded by rank (weak scaling, 16 images per GPU); the packed detections of
+every round of 8 steps are gathered to rank 0 through NVLink peer memory (sharding.PeerGather; NCCL all_gather
+where symmetric memory is unavailable), overlapped with the following rounds; time = max over ranks.
 """
 import argparse
 import json

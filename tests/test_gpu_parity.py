@@ -978,3 +978,41 @@ def test_assign_large_batch_tile_shape():
         assert_equal_int(to_np(got[0][i]), to_np(ref[0][j]), what="cls_t")
         assert np.array_equal(to_np(got[2][i]), to_np(ref[2][j]))
         assert_equal_int(to_np(got[3][i]), to_np(ref[3][j]), what="gt index")
+
+
+# ------------------------------------------------------------------------------------------
+# multi-GPU gather through peer memory (one rank here; bench.py under torchrun runs it at 2 / 8 GPUs)
+# ------------------------------------------------------------------------------------------
+def test_peer_gather_single_rank_roundtrip():
+    """sharding.PeerGather on a one-rank group: symmetric-memory rendezvous, the copy-engine push into the
+    rank's own slot, the device-side barrier and slot rotation.  Skipped where symmetric memory is unavailable
+    (bench.py then falls back to the NCCL all_gather of sharding.gather_packed)."""
+    import socket
+
+    import torch.distributed as dist
+    from pytorch_object_detection_b200.sharding import PeerGather
+
+    created = False
+    if not dist.is_initialized():
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                                device_id=torch.device(DEV))
+        created = True
+    try:
+        try:
+            pg = PeerGather(4096, 2, torch.device(DEV))
+        except Exception as e:                                 # noqa: BLE001
+            pytest.skip(f"symmetric memory unavailable: {type(e).__name__}: {e}")
+        gen = torch.Generator(device=DEV).manual_seed(3)
+        for slot, root in ((0, None), (1, 0), (0, 0)):
+            src = torch.randint(0, 256, (4096,), dtype=torch.uint8, device=DEV, generator=gen)
+            view = pg.gather(slot, src, root=root)
+            torch.cuda.synchronize()
+            assert view.shape == (1, 4096) and torch.equal(view[0], src)
+        with pytest.raises(ValueError):
+            pg.gather(0, torch.zeros(8, dtype=torch.uint8, device=DEV))
+    finally:
+        if created:
+            dist.destroy_process_group()
