@@ -76,6 +76,55 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_gpu():
         _lib.check(1, "x")
 
 
+def test_training_step_entry_points_validate_before_launching():
+    """b200det_cls_loss_step / b200det_assign_loss_fused / b200det_rescale_maps: null pointers, unknown
+    grad_mode / dtype, duplicate states and undersized workspaces are refused on the host."""
+    lib = _lib.load()
+    one = C.c_void_p(16)                                                  # a non-null, 16-byte aligned dummy address
+    lv = _lib.make_levels([(16, 16, 16, 4, 4, 8)])
+    grads = (C.c_void_p * 1)(16)
+    ws_bytes = lib.b200det_cls_loss_workspace_bytes(1, 16, 20)
+    step = lambda **kw: lib.b200det_cls_loss_step(                        # noqa: E731
+        lv, kw.get("grads", grads), kw.get("dtype", 0), 1, 1, 20, one, one, None, kw.get("grad_mode", 0), 0,
+        kw.get("ws", one), kw.get("ws_bytes", ws_bytes), one, one, None, None)
+    assert step(grads=None) == 1
+    assert step(grad_mode=2) == 1
+    assert step(dtype=7) == 2                                             # B200DET_ERR_UNSUPPORTED
+    assert step(ws=None) == 1
+    assert step(ws_bytes=4) == 3                                          # B200DET_ERR_WORKSPACE
+    maps = (C.c_void_p * 2)(16, 32)
+    numel = (C.c_int64 * 2)(4, 4)
+    idx = (C.c_int32 * 2)(0, 1)
+    got = (C.c_void_p * 2)(16, 16)
+    states = (C.c_void_p * 2)(64, 128)
+    assert lib.b200det_rescale_maps(maps, numel, idx, 0, 0, got, states, 2, None) == 1        # no maps
+    assert lib.b200det_rescale_maps(maps, numel, idx, 0, 17, got, states, 2, None) == 1       # too many maps
+    assert lib.b200det_rescale_maps(maps, numel, idx, 9, 2, got, states, 2, None) == 2        # unknown dtype
+    assert lib.b200det_rescale_maps(maps, numel, (C.c_int32 * 2)(0, 2), 0, 2, got, states, 2, None) == 1   # state index
+    assert lib.b200det_rescale_maps(maps, numel, idx, 0, 2, got, (C.c_void_p * 2)(64, 64), 2, None) == 1   # duplicate state
+    assert lib.b200det_rescale_maps(maps, numel, idx, 0, 2, got, states, 5, None) == 1        # too many states
+    assert lib.b200det_assign_loss_workspace_bytes(0, 100) == 0
+    lo = (C.c_float * 1)(-1.0)
+    hi = (C.c_float * 1)(64.0)
+    ra = (C.c_float * 1)(12.0)
+    fused = lambda grad_mode, mode=1: lib.b200det_assign_loss_fused(       # noqa: E731
+        lv, grads, None, 1, lo, hi, ra, 1, 0, None, None, mode, None, None, grad_mode, one, one, one, one, None, one,
+        None, None, one, 1 << 20, None)
+    assert fused(2) == 2 and fused(0, mode=5) == 2
+    # the half-precision class maps of autocast keep their dtype through the Python level table only when asked
+    from pytorch_object_detection_b200 import ops
+    assert ops._DTYPE_CODE == {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def test_upstream_state_is_lazy_and_per_device():
+    from pytorch_object_detection_b200.loss import _Upstream
+    up = _Upstream()
+    assert up.observed is False and up._value == {}
+    step = P.FCOSTargetLoss(W.STRIDES, W.FCOS_RANGES, "giou")
+    assert all(isinstance(u, _Upstream) for u in (step._up_cls, step._up_box, step._up_cnt))
+    assert isinstance(P.FCOSLoss()._up_cls, _Upstream)
+
+
 def test_modules_have_no_cpu_path_and_keep_reference_errors():
     x = W.head_outputs(1, 20, W.VOC_LEVELS, seed=3)
     head = P.FCOSHead(0.05, 0.6, 1000, W.STRIDES)
