@@ -473,28 +473,42 @@ __device__ __forceinline__ void rescale_map(T* m, const long long n, const float
 
 template <typename T>
 __global__ void __launch_bounds__(256) rescale_maps_kernel(const RescaleTable t, const int n_maps, const int n_states) {
-  __shared__ float s_f[kMaxStates];
-  if (threadIdx.x < n_states) {
-    const float got = __ldcg(t.got[threadIdx.x]), assumed = __ldcg(t.state[threadIdx.x]);
-    s_f[threadIdx.x] = (got == assumed) ? 1.0f : got / assumed;
+  // every thread reads the (<= 4) pairs itself: the usual launch finds them equal and ends here, without a
+  // barrier or an atomic.  The assumed values only change after ALL CTAs have read them (ticket below), so
+  // every CTA takes the same decision.
+  float f[kMaxStates];
+  bool any = false;
+#pragma unroll
+  for (int s = 0; s < kMaxStates; ++s) {
+    f[s] = 1.0f;
+    if (s < n_states) {
+      const float got = __ldcg(t.got[s]), assumed = __ldcg(t.state[s]);
+      if (got != assumed) {
+        f[s] = got / assumed;
+        any = true;
+      }
+    }
   }
-  __syncthreads();
+  if (!any) return;
   const long long step = (long long)gridDim.x * 256;
   const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
   for (int i = 0; i < n_maps; ++i) {
-    const float f = s_f[t.state_of[i]];
-    if (f != 1.0f) rescale_map(static_cast<T*>(t.map[i]), t.numel[i], f, i0, step);
+    const int so = t.state_of[i];
+    const float fi = so == 0 ? f[0] : so == 1 ? f[1] : so == 2 ? f[2] : f[3];
+    if (fi != 1.0f) rescale_map(static_cast<T*>(t.map[i]), t.numel[i], fi, i0, step);
   }
   // remember the upstream gradient that arrived (a zero / non-finite one is not a usable assumption for the
-  // next forward: its gradients could not be rescaled)
+  // next forward: its gradients could not be rescaled); only states that differed take part
   __syncthreads();
   if (threadIdx.x < n_states) {
-    unsigned* ticket = reinterpret_cast<unsigned*>(t.state[threadIdx.x] + 1);
-    __threadfence();
-    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
-      const float g = __ldcg(t.got[threadIdx.x]);
-      if (g != 0.f && isfinite(g)) *t.state[threadIdx.x] = g;
-      *ticket = 0u;
+    const float g = __ldcg(t.got[threadIdx.x]);
+    if (g != __ldcg(t.state[threadIdx.x])) {
+      unsigned* ticket = reinterpret_cast<unsigned*>(t.state[threadIdx.x] + 1);
+      __threadfence();
+      if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        if (g != 0.f && isfinite(g)) *t.state[threadIdx.x] = g;
+        *ticket = 0u;
+      }
     }
   }
 }
