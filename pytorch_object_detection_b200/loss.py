@@ -85,7 +85,8 @@ class _Upstream:
         key = (device.type, device.index)
         v = self._value.get(key)
         if v is None:
-            v = torch.tensor([1.0, 0.0], dtype=torch.float32, device=device)     # {assumed, ticket}
+            v = torch.zeros(2, dtype=torch.float32, device=device)               # {assumed, ticket}
+            v[:1].fill_(1.0)                                                       # (fill kernels only: capturable)
             if not torch.cuda.is_current_stream_capturing():
                 self._value[key] = v
         return v
