@@ -149,3 +149,39 @@ def test_eval_oracle_matches_reference_ap(name):
                     [l[o] for l, o in zip(lists["det_labels"], order)],
                     [s[o] for s, o in zip(lists["det_scores"], order)], thr, num_cls)
     assert_ap_equal([got[c] for c in range(1, num_cls)], want, what=name)
+
+
+def test_focal_step_gradient_identity_matches_reference_autograd():
+    """The focal step kernel writes the gradient of a non-target element as 0.75 om pr (om - 2 pt log pt) with
+    pt = fl(1 - p), om = fl(1 - pt) (csrc/loss.cu, focal_neg_both_nb2): no reciprocal, every intermediate
+    shared with the loss.  Restated here in fp32 numpy with exact transcendentals and checked against autograd
+    of the reference's formula (loss.py:180-193) over logits in [-30, 14]: the identity itself is exact to fp32
+    rounding, what remains for the GPU test is the accuracy of MUFU.EX2 / RCP / LG2."""
+    f = np.float32
+    x = np.linspace(-30, 14, 200001).astype(f)
+    xt = torch.tensor(x, requires_grad=True)
+    p = torch.sigmoid(xt).clip(min=0.000005, max=0.99999999995)
+    pt = 1.0 - p                                                          # y = 0: pt = 1 - p, w = 0.75
+    loss = -0.75 * torch.pow(1.0 - pt, 2.0) * torch.log(pt)
+    loss.sum().backward()
+    want_g = xt.grad.numpy().astype(np.float64)
+    want_l = loss.detach().numpy().astype(np.float64)
+    pr = torch.sigmoid(torch.tensor(x)).numpy()
+    pc = np.maximum(pr, f(0.000005))
+    ptn = (f(1) - pc).astype(f)
+    om = (f(1) - ptn).astype(f)
+    lg = np.log(ptn.astype(np.float64)).astype(f)
+    t = (om.astype(np.float64) - 2.0 * lg.astype(np.float64) * ptn.astype(np.float64)).astype(f)   # one fma
+    g = ((f(0.75) * (om * pr).astype(f)).astype(f) * t).astype(f)
+    g = np.where(pr >= f(0.000005), g, f(0))
+    l = ((f(-0.75) * (om * om).astype(f)).astype(f) * lg).astype(f)
+    big = np.abs(want_g) > 1e-12
+    assert np.max(np.abs(g[big] - want_g[big]) / np.abs(want_g[big])) < 2e-6
+    assert np.all(g[~big & (pr < f(0.000005))] == 0)                      # clip: no gradient below 5e-6
+    ok = np.abs(want_l) > 1e-30
+    assert np.max(np.abs(l[ok] - want_l[ok]) / np.abs(want_l[ok])) < 2e-6
+    # the series the kernel uses for log(pt) where om <= 1/16: -om * (1 + om/2 + ... + om^6/7)
+    u = np.linspace(0, 0.0625, 10001)
+    series = -u * sum(u ** k / (k + 1) for k in range(7))
+    exact = np.log1p(-u)
+    assert np.max(np.abs(series[1:] - exact[1:]) / np.abs(exact[1:])) < 2e-9
