@@ -235,6 +235,7 @@ def main():
     # are gathered to rank 0, where an evaluation collects them (Test_coco.py:144-168 writes one result file);
     # B200DET_BENCH_GATHER=peer_all gives every rank every detection instead (8 GPUs: 24.2 us per step).
     peer = None
+    gather_check = {"ok": None}                             # peer gather compared with NCCL all_gather once
     gather_kind = "none"
     if dist is not None:
         gather_kind = "NCCL all_gather"
@@ -325,6 +326,24 @@ def main():
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t[0])
+        if peer is not None and gather_check["ok"] is None:
+            # outside the timed region, once: what the peer-memory gather delivered to its receivers must be what
+            # an NCCL all_gather of the same buffers delivers (every rank takes part in both)
+            try:
+                g, out_big, _ = rounds[0]
+                g.replay()
+                ref = torch.empty((world, out_big.numel()), dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(ref, out_big.reshape(-1))
+                got = peer.gather(0, out_big.reshape(-1), root=gather_root)
+                torch.cuda.synchronize()
+                same = torch.tensor([1.0], device=dev)
+                if gather_root is None or rank == gather_root:
+                    same[0] = 1.0 if torch.equal(got, ref) else 0.0
+                dist.all_reduce(same, op=dist.ReduceOp.MIN)
+                gather_check["ok"] = bool(float(same[0]) == 1.0)
+            except Exception as e:                          # noqa: BLE001  (never lose the measurement to the check)
+                print(f"[bench] rank {rank}: gather check failed to run: {type(e).__name__}: {e}", file=sys.stderr)
+                gather_check["ok"] = False
         return ms / args.steps, args.steps
 
     # ---- value: device-resident, `n_streams` batches in flight; and one batch at a time ------------
@@ -565,7 +584,8 @@ def main():
             "config": {"workload": WORKLOAD, "global_batch": world * BATCH,
                        "l2": f"{args.sets} input sets of {in_bytes / 1e6:.0f} MB rotated (> 126 MB L2)",
                        "in_flight": f"{n_streams} batches on {n_streams} CUDA streams inside one CUDA graph of {args.sets} steps",
-                       "collective": f"one gather of the packed detections per {args.sets} steps, overlapped: {gather_kind}" if world > 1 else "none"},
+                       "collective": f"one gather of the packed detections per {args.sets} steps, overlapped: {gather_kind}" if world > 1 else "none",
+                       "gather_equals_nccl_all_gather": gather_check["ok"]},
             "single_stream": {"value": world * BATCH / (ms_single * 1e-3), "unit": "img/s", "ms_per_step": ms_single},
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "steps": e2e_steps, "api": "FCOSHead.detect(clip_hw=...) on pinned host inputs"},
