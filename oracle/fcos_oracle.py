@@ -29,10 +29,11 @@ CPU_TRICK_MAX_NUMEL = 4000  # torchvision ops/boxes.py batched_nms, CPU threshol
 # --------------------------------------------------------------------------------------
 # grid / layout                                                        utill/utills.py:58-73
 # --------------------------------------------------------------------------------------
-def grid_points(h: int, w: int, stride: int) -> Tensor:
-    """Row-major point grid (x, y) = (j*s + s//2, i*s + s//2) as fp32 [h*w, 2]."""
-    xs = torch.arange(0, w * stride, stride, dtype=torch.float32)
-    ys = torch.arange(0, h * stride, stride, dtype=torch.float32)
+def grid_points(h: int, w: int, stride: int, device=None) -> Tensor:
+    """Row-major point grid (x, y) = (j*s + s//2, i*s + s//2) as fp32 [h*w, 2] (``device``: where the
+    reference builds it, head.py:22 — only bench.py's informative eager-on-GPU leg passes a CUDA device)."""
+    xs = torch.arange(0, w * stride, stride, dtype=torch.float32, device=device)
+    ys = torch.arange(0, h * stride, stride, dtype=torch.float32, device=device)
     yy, xx = torch.meshgrid(ys, xs, indexing="ij")
     return torch.stack([xx.reshape(-1), yy.reshape(-1)], dim=-1) + stride // 2
 
@@ -43,7 +44,7 @@ def flatten_levels(levels: Sequence[Tensor], strides: Sequence[int]) -> Tuple[Te
     b, c = levels[0].shape[0], levels[0].shape[1]
     for lvl, s in zip(levels, strides):
         nhwc = lvl.permute(0, 2, 3, 1)
-        pts.append(grid_points(nhwc.shape[1], nhwc.shape[2], s))
+        pts.append(grid_points(nhwc.shape[1], nhwc.shape[2], s, lvl.device))
         flat.append(nhwc.reshape(b, -1, c))
     return torch.cat(flat, dim=1), torch.cat(pts, dim=0)
 
@@ -168,7 +169,7 @@ def assign_level(h: int, w: int, gt: Tensor, labels: Tensor, stride: int,
     Returns cls_t [B, hw, 1] int64, cnt_t [B, hw, 1] f32, reg_t [B, hw, 4] f32 and, for
     tests, the chosen GT index [B, hw] (argmin of masked area, -1 where negative).
     """
-    pts = grid_points(h, w, stride)
+    pts = grid_points(h, w, stride, gt.device)
     px, py = pts[:, 0:1], pts[:, 1:2]                                    # [hw, 1]
     cls_o, cnt_o, reg_o, idx_o = [], [], [], []
     for b in range(gt.shape[0]):
@@ -189,7 +190,7 @@ def assign_level(h: int, w: int, gt: Tensor, labels: Tensor, stride: int,
         pos = in_box & in_lvl & (cmax < stride * radius)                 # head.py:275-283
         area = torch.where(pos, area, torch.full_like(area, AREA_SENTINEL))  # head.py:285
         pick = area.min(dim=-1)[1]                                       # first index on ties
-        rows = torch.arange(pick.numel())
+        rows = torch.arange(pick.numel(), device=pick.device)
         reg = off[rows, pick]                                            # head.py:287-288
         cls = labels[b][pick]                                            # head.py:290-292
         lr_min, lr_max = torch.min(reg[:, 0], reg[:, 2]), torch.max(reg[:, 0], reg[:, 2])
@@ -256,7 +257,7 @@ def cls_loss(cls_levels, cls_t: Tensor, mask: Tensor) -> Tensor:
     logits = _flat(cls_levels, c)
     assert logits.shape[:2] == cls_t.shape[:2]
     npos = mask.sum(dim=1).clamp(min=1).float()
-    ids = torch.arange(1, c + 1)[None, :]
+    ids = torch.arange(1, c + 1, device=cls_t.device)[None, :]
     out = [focal_sum(logits[b], (ids == cls_t[b]).float()).view(1) for b in range(logits.shape[0])]
     return torch.cat(out) / npos
 

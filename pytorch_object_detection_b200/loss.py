@@ -145,20 +145,30 @@ class _TapUpstream(torch.autograd.Function):
 
 
 def _cls_loss_mean(preds: List[Tensor], cls_t: Tensor, mask_src: Tensor | None, num_pos: Tensor | None,
-                   up: _Upstream) -> Tensor:
+                   up: _Upstream, per_image: dict | None = None) -> Tensor:
     """``compute_cls_loss(...).mean()`` (loss.py:210).  When a gradient will be asked for, the forward kernel
-    writes it too (238 MB read once instead of twice at COCO batch 32); otherwise the forward kernel alone runs."""
+    writes it too (238 MB read once instead of twice at COCO batch 32); otherwise the forward kernel alone runs.
+    ``per_image["cls"]`` receives the detached per-image losses [B] (what a multi-rank run reduces)."""
     _check_points(preds, cls_t)                                    # loss.py:18
     if torch.is_grad_enabled() and any(t.requires_grad for t in preds):
         half = preds[0].dtype in (torch.float16, torch.bfloat16)
         if not half or up.observed:
-            return _ClsLossStep.apply(cls_t, mask_src, num_pos, up, *preds)[0]
+            mean, loss, _ = _ClsLossStep.apply(cls_t, mask_src, num_pos, up, *preds)
+            if per_image is not None:
+                per_image["cls"] = loss
+            return mean
         # half-precision logits, first step: the loss scale is not known yet -> forward and backward kernels
         if mask_src is not None:
-            return _TapUpstream.apply(_ClsLoss.apply(mask_src, cls_t, *preds).mean(), up)
+            loss = _ClsLoss.apply(mask_src, cls_t, *preds)
+            if per_image is not None:
+                per_image["cls"] = loss.detach()
+            return _TapUpstream.apply(loss.mean(), up)
     if mask_src is None:
         raise ValueError("the forward-only focal loss needs the positive-mask source (cnt_t)")
-    return _ClsLoss.apply(mask_src, cls_t, *preds).mean()
+    loss = _ClsLoss.apply(mask_src, cls_t, *preds)
+    if per_image is not None:
+        per_image["cls"] = loss.detach()
+    return loss.mean()
 
 
 def _check_points(preds: Sequence[Tensor], target: Tensor) -> None:
@@ -343,6 +353,7 @@ class FCOSTargetLoss(nn.Module):
         reg_loss, cnt_loss = self.box_cnt_losses(cnt_logits, reg_preds, gt_boxes, labels)
         cls_t, cnt_t, _ = self.targets
         n = min(len(self.strides), len(cls_logits))
-        cls_loss = _cls_loss_mean(list(cls_logits[:n]), cls_t, cnt_t, self.per_image["num_pos"], self._up_cls)
+        cls_loss = _cls_loss_mean(list(cls_logits[:n]), cls_t, cnt_t, self.per_image["num_pos"], self._up_cls,
+                                  self.per_image)
         total_loss = cls_loss + cnt_loss + reg_loss
         return cls_loss, cnt_loss, reg_loss, total_loss

@@ -87,8 +87,8 @@ class PeerGather:
 
     Measured against NCCL ``all_gather`` in ``bench.py`` (the NCCL kernel's duration is exposed: its CTAs wait
     for SM resources behind the saturating post-process kernels).  ``slots`` receive buffers rotate so that a
-    consumer may read slot q while later gathers fill the others; consume a slot in stream order before
-    ``gather`` is called ``slots`` more times.  Needs P2P-capable GPUs of one node (NVLink / NVSwitch) and a
+    consumer may read slot q while later gathers fill the others (hence ``slots >= 2``); consume a slot in
+    stream order before ``gather`` is called ``slots - 1`` more times.  Needs P2P-capable GPUs of one node (NVLink / NVSwitch) and a
     ``torch.distributed`` process group with one rank per GPU; raises if symmetric memory is unavailable
     (callers fall back to ``gather_packed``).  All ranks must call ``gather`` in the same order.
     """
@@ -100,6 +100,10 @@ class PeerGather:
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.nbytes, self.slots = int(nbytes), int(slots)
+        if self.slots < 2:
+            # with one slot a peer's next push is ordered after this rank REACHED the previous barrier, not after it
+            # finished reading the slot: the returned view could be overwritten while it is read
+            raise ValueError("PeerGather needs slots >= 2 (a slot is reused only after `slots` further gathers)")
         shape = (self.slots, self.world, self.nbytes)
         self.recv = symm_mem.empty(shape, dtype=torch.uint8, device=device)
         self.handle = symm_mem.rendezvous(self.recv, self.group)
@@ -124,9 +128,17 @@ class PeerGather:
 
 
 def packed_of(scores: Tensor) -> Tensor:
-    """The packed uint8 buffer behind the outputs of ``ops.postprocess`` / ``FCOSHead.detect``."""
+    """The packed uint8 buffer behind the outputs of ``ops.postprocess`` / ``FCOSHead.detect``: it starts at the
+    scores tensor ([B, K] fp32, the first member of the layout) and spans ``ops.packed_nbytes(B, K)`` bytes — also
+    when the caller placed it inside a larger allocation (``out_packed`` slices)."""
+    from . import ops
+    batch, k = scores.shape
     st = scores.untyped_storage()
-    return torch.empty(0, dtype=torch.uint8, device=scores.device).set_(st, 0, (st.nbytes(),))
+    start = scores.storage_offset() * scores.element_size()
+    n = ops.packed_nbytes(batch, k)
+    if start + n > st.nbytes():
+        raise ValueError("scores is not the first member of a packed detection buffer")
+    return torch.empty(0, dtype=torch.uint8, device=scores.device).set_(st, start, (n,))
 
 
 def reduce_image_losses(per_image: Sequence[Tensor], batch: int, group=None) -> List[Tensor]:
@@ -135,9 +147,6 @@ def reduce_image_losses(per_image: Sequence[Tensor], batch: int, group=None) -> 
     Exact with respect to the reference's ``.mean()`` over the batch up to fp32 summation order,
     because every loss is normalised per image before the mean (loss.py:26,57,139,209-213).
     """
-    out = []
-    for t in per_image:
-        s = t.sum() / batch
-        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
-        out.append(s)
-    return out
+    sums = torch.stack([t.to(torch.float32).sum() for t in per_image]) / batch      # ONE collective for all losses
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    return list(sums.unbind(0))
