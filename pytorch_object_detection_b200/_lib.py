@@ -79,7 +79,7 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("B200DET_LIB") or _build.LIB      # (B200DET_LIB: a variant build for A/B timing / tracing)
     if not os.path.exists(path):     # staleness is handled by __graft_entry__.build(), not at import
         try:
             _build.build()

@@ -101,9 +101,18 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // ---- optional phase tracing (build with -DB200DET_TRACE; scripts/trace_phases.py reads it) --------
 #ifdef B200DET_TRACE
 #define B200DET_TRACE_BUFFER(name)                                                   \
-  namespace b200det { static __device__ long long g_trace[64]; }                     \
+  namespace b200det { static __device__ long long g_trace[64]; static __device__ long long g_cta[4096 * 2]; } \
+  extern "C" int b200det_debug_read_cta_trace_##name(long long* host_out, int n) {   \
+    return (int)cudaMemcpyFromSymbol(host_out, b200det::g_cta, sizeof(long long) * (n > 8192 ? 8192 : n)); \
+  }                                                                                  \
   extern "C" int b200det_debug_read_trace_##name(long long* host_out, int n) {       \
     return (int)cudaMemcpyFromSymbol(host_out, b200det::g_trace, sizeof(long long) * (n > 64 ? 64 : n)); \
+  }                                                                                  \
+  extern "C" int b200det_debug_reset_trace_##name(void) {                            \
+    long long z_[64];                                                                \
+    for (int i = 0; i < 64; ++i) z_[i] = 0;                                          \
+    z_[60] = 0x7fffffffffffffffll;                                                   \
+    return (int)cudaMemcpyToSymbol(b200det::g_trace, z_, sizeof(z_));                \
   }
 #define B200DET_STAMP(slot)                                                          \
   do {                                                                               \
@@ -118,7 +127,41 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
   do {                                                                               \
     if ((cond) && threadIdx.x == 0) g_trace[slot] = clock64();                       \
   } while (0)
+#define B200DET_NOTE_IF(cond, slot, v)                                               \
+  do {                                                                               \
+    if ((cond) && threadIdx.x == 0) g_trace[slot] = (long long)(v);                  \
+  } while (0)
+#define B200DET_STAMP_ANY(cond, slot)                                                \
+  do {                                                                               \
+    if (cond) g_trace[slot] = clock64();                                             \
+  } while (0)
+/* kernel span in ns of %globaltimer: slot 60 = first CTA start (min), 61 = last CTA end (max), 62 = CTAs that   \
+   recounted; reset by reading the trace */                                          \
+#define B200DET_SPAN_BEGIN()                                                         \
+  do {                                                                               \
+    if (threadIdx.x == 0) {                                                          \
+      unsigned long long t_;                                                         \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                         \
+      atomicMin(reinterpret_cast<unsigned long long*>(&g_trace[60]), t_);            \
+      const unsigned c_ = blockIdx.x + gridDim.x * blockIdx.y;                       \
+      if (c_ < 4096) g_cta[2 * c_] = (long long)t_;                                  \
+    }                                                                                \
+  } while (0)
+#define B200DET_SPAN_END()                                                           \
+  do {                                                                               \
+    if (threadIdx.x == 0) {                                                          \
+      unsigned long long t_;                                                         \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                         \
+      atomicMax(reinterpret_cast<unsigned long long*>(&g_trace[61]), t_);            \
+      const unsigned c_ = blockIdx.x + gridDim.x * blockIdx.y;                       \
+      if (c_ < 4096) g_cta[2 * c_ + 1] = (long long)t_;                              \
+    }                                                                                \
+  } while (0)
 #else
+#define B200DET_NOTE_IF(cond, slot, v) do {} while (0)
+#define B200DET_STAMP_ANY(cond, slot) do {} while (0)
+#define B200DET_SPAN_BEGIN() do {} while (0)
+#define B200DET_SPAN_END() do {} while (0)
 #define B200DET_STAMP_IF(cond, slot) do {} while (0)
 #define B200DET_TRACE_BUFFER(name)
 #define B200DET_STAMP(slot) do {} while (0)

@@ -23,7 +23,7 @@ launch_count = 0          # kernels launched through this module (bench.py repor
 # kernels per C entry point (see csrc/*.cu)
 _LAUNCHES = {"postprocess": 4, "batched_nms": 3, "score_points": 1, "select_topk": 1, "clip_boxes": 1,
              "assign_targets": 1, "box_loss_fwd": 1, "box_loss_bwd": 1, "cnt_loss_fwd": 1, "cnt_loss_bwd": 1,
-             "cls_loss_fwd": 2, "cls_loss_bwd": 1, "cls_loss_step": 2, "count_pos": 1, "assign_loss_fused": 3, "scale_maps": 1, "rescale_maps": 1,
+             "cls_loss_fwd": 2, "cls_loss_bwd": 1, "cls_loss_step": 2, "count_pos": 1, "assign_loss_fused": 2, "scale_maps": 1, "rescale_maps": 1,
              "pack_gt": 1, "collate_images": 1, "eval_ap": 2, "coco_boxes": 1}
 
 
