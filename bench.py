@@ -729,13 +729,26 @@ def strong_scaling_leg(B, ops, sharding, dist, dev, rank, world, barrier, max_ov
     head = B.FCOSHead(SCORE_THR, NMS_THR, MAX_BOX, W.STRIDES)
     step = B.FCOSTargetLoss(W.STRIDES, W.HISFCOS_RANGES, "giou")
     k_out = min(MAX_BOX, P)
-    pk = torch.empty((ops.packed_nbytes(nb, k_out),), dtype=torch.uint8, device=dev)
+    # the shard is post-processed in micro-batches of 16 forked over up to 8 streams (K1 of one overlaps the
+    # per-image select/NMS CTAs of the others, as in the weak-scaling loop); their packed outputs share ONE buffer
+    spans = [(i, min(i + BATCH, nb)) for i in range(0, nb, BATCH)]
+    sizes = [ops.packed_nbytes(hi_ - lo_, k_out) for lo_, hi_ in spans]
+    pk = torch.empty((sum(sizes),), dtype=torch.uint8, device=dev)
     full = torch.empty((world, pk.numel()), dtype=torch.uint8, device=dev) if world > 1 else None
-    x_det = [[t.detach() for t in part] for part in (cls, cnt, reg)]
+    offs = [sum(sizes[:i]) for i in range(len(sizes))]
+    x_mb = [[[t.detach()[lo_:hi_] for t in part] for part in (cls, cnt, reg)] for lo_, hi_ in spans]
+    post_streams = [torch.cuda.Stream(device=dev) for _ in range(min(8, len(spans)))]
     side = torch.cuda.Stream(device=dev)
 
     def post(_i=0):
-        head.detect(x_det, clip_hw=W.COCO_HW, out_packed=pk)
+        cur = torch.cuda.current_stream()
+        for st in post_streams:
+            st.wait_stream(cur)
+        for j, x_j in enumerate(x_mb):
+            with torch.cuda.stream(post_streams[j % len(post_streams)]):
+                head.detect(x_j, clip_hw=W.COCO_HW, out_packed=pk[offs[j]:offs[j] + sizes[j]])
+        for st in post_streams:
+            cur.wait_stream(st)
 
     def train(_i=0):
         for t in cls + cnt + reg:

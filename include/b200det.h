@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define B200DET_ABI_VERSION 5
+#define B200DET_ABI_VERSION 6
 #define B200DET_MAX_LEVELS 8
 #define B200DET_MAX_BOX 8192      /* largest max_detection_box / NMS candidate count per image */
 
@@ -58,9 +58,17 @@ typedef struct {
   const void* cls;
   const void* cnt;
   const void* reg;
-  int32_t h, w, stride, pad_;
+  int32_t h, w, stride;
+  int32_t dtypes;                 /* B200DET_LEVEL_DTYPES(cls_cnt, reg); 0 = everything fp32 */
   const void* reg_scale;
 } b200det_level;
+
+/* Element types of a level's maps: `cls_cnt` for the cls and cnt maps, `reg` for the reg map (b200det_dtype each).
+ * Honoured by b200det_score_points / b200det_select_topk / b200det_postprocess, which read the fp16 / bf16 head
+ * outputs of an autocast forward (train.py:175) as they are and evaluate in fp32 — bit-identical to the fp32 kernels
+ * on up-cast inputs, without the up-cast pass.  All levels of a call must agree.  Every other entry point takes
+ * fp32 maps (dtypes == 0) unless it has a dtype argument of its own. */
+#define B200DET_LEVEL_DTYPES(cls_cnt, reg) ((int32_t)(cls_cnt) | ((int32_t)(reg) << 4))
 
 int         b200det_abi_version(void);
 const char* b200det_status_string(int status);
@@ -72,7 +80,8 @@ const char* b200det_last_cuda_error(void);
  * ------------------------------------------------------------------------------------- */
 
 /* K1 — head.py:8-26,57-63 without the NHWC copy: per point
- *   score = sqrt(max_c sigmoid(cls) * sigmoid(cnt)),  cls0 = argmax_c (first index on ties),
+ *   score = sqrt(max_c sigmoid(cls) * sigmoid(cnt)),  cls0 = argmax_c sigmoid(cls) with torch.max's first index
+ * among EQUAL fp32 sigmoid values (distinct logits can share one: saturated or a few ulps apart, head.py:57-62),
  * written level-major as score[B,P] f32 and cls0[B,P] int16 (0-based). */
 int b200det_score_points(const b200det_level* levels, int n_levels, int batch, int num_classes,
                          float* score, int16_t* cls0, void* stream);

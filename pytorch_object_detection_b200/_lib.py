@@ -14,13 +14,13 @@ from . import build as _build
 
 MAX_LEVELS = 8
 MAX_BOX = 8192
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class Level(C.Structure):
     """``b200det_level``."""
     _fields_ = [("cls", C.c_void_p), ("cnt", C.c_void_p), ("reg", C.c_void_p),
-                ("h", C.c_int32), ("w", C.c_int32), ("stride", C.c_int32), ("pad_", C.c_int32),
+                ("h", C.c_int32), ("w", C.c_int32), ("stride", C.c_int32), ("dtypes", C.c_int32),
                 ("reg_scale", C.c_void_p)]
 
 
@@ -105,12 +105,13 @@ def check(status: int, what: str) -> None:
         raise B200DetError(f"{what}: {msg}")
 
 
-def make_levels(entries: Sequence[tuple]) -> C.Array:
-    """entries: (cls_ptr, cnt_ptr, reg_ptr, h, w, stride[, reg_scale_ptr]) per level; pointers may be 0/None."""
+def make_levels(entries: Sequence[tuple], dtypes: int = 0) -> C.Array:
+    """entries: (cls_ptr, cnt_ptr, reg_ptr, h, w, stride[, reg_scale_ptr]) per level; pointers may be 0/None.
+    ``dtypes``: B200DET_LEVEL_DTYPES(cls_cnt, reg) = cls_cnt | reg << 4 (0 = fp32 maps)."""
     if not 0 < len(entries) <= MAX_LEVELS:
         raise B200DetError(f"between 1 and {MAX_LEVELS} levels are supported, got {len(entries)}")
     arr = (Level * len(entries))()
     for i, e in enumerate(entries):
         a, b, c, h, w, s = e[:6]
-        arr[i] = Level(a or None, b or None, c or None, h, w, s, 0, (e[6] if len(e) > 6 else None) or None)
+        arr[i] = Level(a or None, b or None, c or None, h, w, s, int(dtypes), (e[6] if len(e) > 6 else None) or None)
     return arr

@@ -1,6 +1,8 @@
 // Shared device/host helpers for the b200det kernels (sm_100a only).
 #pragma once
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -33,6 +35,8 @@ struct LevelTable {
   int tile_off[B200DET_MAX_LEVELS + 1];    // prefix sum of ceil(hw / kTile)
   int n_levels;
   int num_points;
+  int cls_dtype;                           // b200det_dtype of the cls AND cnt maps (b200det_level.dtypes, all levels agree)
+  int reg_dtype;                           // b200det_dtype of the reg maps
 };
 
 // Gradient destinations, one per level (same NCHW shape as the map they belong to).
@@ -52,10 +56,13 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // Returns false on bad arguments.
 inline bool make_level_table(const b200det_level* levels, int n_levels, LevelTable* t) {
   if (!levels || n_levels <= 0 || n_levels > B200DET_MAX_LEVELS) return false;
+  t->cls_dtype = levels[0].dtypes & 15;
+  t->reg_dtype = (levels[0].dtypes >> 4) & 15;
+  if (t->cls_dtype > B200DET_BF16 || t->reg_dtype > B200DET_BF16 || (levels[0].dtypes >> 8)) return false;
   long long off = 0;
   int toff = 0;
   for (int l = 0; l < n_levels; ++l) {
-    if (levels[l].h <= 0 || levels[l].w <= 0 || levels[l].stride <= 0) return false;
+    if (levels[l].h <= 0 || levels[l].w <= 0 || levels[l].stride <= 0 || levels[l].dtypes != levels[0].dtypes) return false;
     t->cls[l] = static_cast<const float*>(levels[l].cls);
     t->cnt[l] = static_cast<const float*>(levels[l].cnt);
     t->reg[l] = static_cast<const float*>(levels[l].reg);
@@ -64,6 +71,8 @@ inline bool make_level_table(const b200det_level* levels, int n_levels, LevelTab
     t->w[l] = levels[l].w;
     t->stride[l] = levels[l].stride;
     t->hw[l] = levels[l].h * levels[l].w;
+    // 4 consecutive elements per access: 16 bytes of fp32, 8 bytes of fp16 / bf16 (16-byte aligned bases keep every
+    // plane aligned when hw % 4 == 0)
     t->vec_ok[l] = (t->hw[l] % 4 == 0) && aligned16(levels[l].cls) && aligned16(levels[l].cnt) &&
                    aligned16(levels[l].reg);
     t->point_off[l] = static_cast<int>(off);
@@ -82,6 +91,13 @@ inline bool make_level_table(const b200det_level* levels, int n_levels, LevelTab
   }
   t->n_levels = n_levels;
   t->num_points = static_cast<int>(off);
+  return true;
+}
+
+// entry points without half-precision kernels: every level must declare fp32 maps
+inline bool fp32_levels(const b200det_level* levels, int n_levels) {
+  for (int l = 0; levels && l < n_levels; ++l)
+    if (levels[l].dtypes != 0) return false;
   return true;
 }
 
@@ -188,6 +204,54 @@ __device__ __forceinline__ float ldg_stream_f1(const float* p) {
   asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
 }
+// 4 consecutive 16-bit elements (8 bytes) / one element, streaming, as raw bits
+__device__ __forceinline__ uint2 ldg_stream_b64(const void* p) {
+  uint2 r;
+  asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ unsigned short ldg_stream_b16(const void* p) {
+  unsigned short r;
+  asm("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+  return r;
+}
+
+// Element access of a map that may be fp32, fp16 or bf16 (fp32 arithmetic everywhere: a half value is up-cast
+// exactly, so a kernel reading half maps equals the fp32 kernel on up-cast maps bit for bit).
+template <typename T> struct MapElem;
+template <> struct MapElem<float> {
+  static __device__ __forceinline__ float4 load4(const void* base, size_t i) { return ldg_stream_f4(static_cast<const float*>(base) + i); }
+  static __device__ __forceinline__ float load1(const void* base, size_t i) { return ldg_stream_f1(static_cast<const float*>(base) + i); }
+};
+template <> struct MapElem<__half> {
+  static __device__ __forceinline__ float4 load4(const void* base, size_t i) {
+    const uint2 r = ldg_stream_b64(static_cast<const __half*>(base) + i);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ float load1(const void* base, size_t i) {
+    const unsigned short r = ldg_stream_b16(static_cast<const __half*>(base) + i);
+    return __half2float(*reinterpret_cast<const __half*>(&r));
+  }
+};
+template <> struct MapElem<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 load4(const void* base, size_t i) {
+    const uint2 r = ldg_stream_b64(static_cast<const __nv_bfloat16*>(base) + i);
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                       __uint_as_float(r.y & 0xffff0000u));
+  }
+  static __device__ __forceinline__ float load1(const void* base, size_t i) {
+    return __uint_as_float((unsigned)ldg_stream_b16(static_cast<const __nv_bfloat16*>(base) + i) << 16);
+  }
+};
+// one element of a map whose type is only known at run time (gathers of a few points)
+__device__ __forceinline__ float load_map_elem(const void* base, const int dtype, const size_t i) {
+  if (dtype == B200DET_F16) return __half2float(static_cast<const __half*>(base)[i]);
+  if (dtype == B200DET_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(base)[i]);
+  return static_cast<const float*>(base)[i];
+}
+
 // streaming (write-once) stores
 __device__ __forceinline__ void stg_stream_f4(float* p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");

@@ -5,33 +5,41 @@
 // level of one image and walks the C class planes, which are contiguous along hw, so every warp
 // load is a full 512-byte run.  sigmoid is monotone, so max_c sigmoid(x_c) = sigmoid(max_c x_c):
 // only the running max of the logits is kept (strict '>' in ascending class order = torch.max's
-// first-index rule) and ONE sigmoid per point is evaluated.  HBM-bound: (C+1)*4 bytes read and
-// 6 bytes written per point.
+// first-index rule) and ONE sigmoid per point is evaluated — two with the check that no other logit shares
+// the winner's fp32 sigmoid (see upd).  fp16 / bf16 maps (autocast) are read as they are.  HBM-bound:
+// (C+1)*4 bytes read and 6 bytes written per point.
 #include "common.cuh"
 
 namespace b200det {
 namespace {
 
-constexpr int kUnroll = 8;   // independent 16-byte loads in flight per thread
+constexpr int kUnroll = 8;   // independent 16-byte (fp32) / 8-byte (fp16, bf16) loads in flight per thread
 
-__device__ __forceinline__ void upd(float& best, int& arg, float v, int c) {
+// Running maximum of the LOGITS with torch.max's first index (strict '>' in ascending class order), plus the second
+// largest value (equal values count): the epilogue needs it to tell whether ANOTHER logit shares the winner's fp32
+// sigmoid, in which case the reference's argmax over sigmoid(cls) (head.py:57-62) may be an earlier class.
+__device__ __forceinline__ void upd(float& best, float& second, int& arg, float v, int c) {
+  second = fmaxf(second, fminf(v, best));
   if (v > best) {
     best = v;
     arg = c;
   }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kTileThreads, 4)
 score_points_kernel(const LevelTable lt, const int C, float* __restrict__ score, int16_t* __restrict__ cls0) {
+  using E = MapElem<T>;
   const int b = blockIdx.y;
   const int l = level_of_tile(lt, blockIdx.x);
   const int hw = lt.hw[l];
   const int t0 = (blockIdx.x - lt.tile_off[l]) * kTile;
-  const float* __restrict__ cls = lt.cls[l] + (size_t)b * C * hw;
-  const float* __restrict__ cnt = lt.cnt[l] + (size_t)b * hw;
+  const void* __restrict__ cls = static_cast<const T*>(static_cast<const void*>(lt.cls[l])) + (size_t)b * C * hw;
+  const void* __restrict__ cnt = static_cast<const T*>(static_cast<const void*>(lt.cnt[l])) + (size_t)b * hw;
   const size_t out0 = (size_t)b * lt.num_points + lt.point_off[l];
 
   float best[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+  float second[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
   int arg[4] = {0, 0, 0, 0};
   int pos[4];
   float cn[4];
@@ -41,28 +49,27 @@ score_points_kernel(const LevelTable lt, const int C, float* __restrict__ score,
     if (p0 >= hw) return;                    // hw % 4 == 0: a 4-group is all in or all out
 #pragma unroll
     for (int q = 0; q < 4; ++q) pos[q] = p0 + q;
-    const float* p = cls + p0;
     int c = 0;
     for (; c + kUnroll <= C; c += kUnroll) {
       float4 v[kUnroll];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) v[u] = ldg_stream_f4(p + (size_t)(c + u) * hw);
+      for (int u = 0; u < kUnroll; ++u) v[u] = E::load4(cls, (size_t)(c + u) * hw + p0);
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        upd(best[0], arg[0], v[u].x, c + u);
-        upd(best[1], arg[1], v[u].y, c + u);
-        upd(best[2], arg[2], v[u].z, c + u);
-        upd(best[3], arg[3], v[u].w, c + u);
+        upd(best[0], second[0], arg[0], v[u].x, c + u);
+        upd(best[1], second[1], arg[1], v[u].y, c + u);
+        upd(best[2], second[2], arg[2], v[u].z, c + u);
+        upd(best[3], second[3], arg[3], v[u].w, c + u);
       }
     }
     for (; c < C; ++c) {
-      const float4 v = ldg_stream_f4(p + (size_t)c * hw);
-      upd(best[0], arg[0], v.x, c);
-      upd(best[1], arg[1], v.y, c);
-      upd(best[2], arg[2], v.z, c);
-      upd(best[3], arg[3], v.w, c);
+      const float4 v = E::load4(cls, (size_t)c * hw + p0);
+      upd(best[0], second[0], arg[0], v.x, c);
+      upd(best[1], second[1], arg[1], v.y, c);
+      upd(best[2], second[2], arg[2], v.z, c);
+      upd(best[3], second[3], arg[3], v.w, c);
     }
-    const float4 cv = ldg_stream_f4(cnt + p0);
+    const float4 cv = E::load4(cnt, p0);
     cn[0] = cv.x; cn[1] = cv.y; cn[2] = cv.z; cn[3] = cv.w;
   } else {
     // planes not 16-byte aligned (e.g. 13x21 = 273): coalesced scalar loads, 4 strided points
@@ -80,21 +87,20 @@ score_points_kernel(const LevelTable lt, const int C, float* __restrict__ score,
       for (int u = 0; u < kUnroll; ++u)
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          v[u][q] = in[q] ? ldg_stream_f1(cls + (size_t)(c + u) * hw + pos[q]) : -CUDART_INF_F;
+          v[u][q] = in[q] ? E::load1(cls, (size_t)(c + u) * hw + pos[q]) : -CUDART_INF_F;
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) upd(best[q], arg[q], v[u][q], c + u);
+        for (int q = 0; q < 4; ++q) upd(best[q], second[q], arg[q], v[u][q], c + u);
     }
     for (; c < C; ++c) {
-      const float* p = cls + (size_t)c * hw;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (in[q]) upd(best[q], arg[q], ldg_stream_f1(p + pos[q]), c);
+        if (in[q]) upd(best[q], second[q], arg[q], E::load1(cls, (size_t)c * hw + pos[q]), c);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      cn[q] = in[q] ? ldg_stream_f1(cnt + pos[q]) : 0.f;
+      cn[q] = in[q] ? E::load1(cnt, pos[q]) : 0.f;
       if (!in[q]) pos[q] = -1;
     }
   }
@@ -102,10 +108,21 @@ score_points_kernel(const LevelTable lt, const int C, float* __restrict__ score,
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     if (pos[q] < 0) continue;
-    // head.py:57-63: sqrt(max_c sigmoid(cls) * sigmoid(cnt)), one rounding per operation
-    const float s = __fsqrt_rn(__fmul_rn(sigmoid_f32(best[q]), sigmoid_f32(cn[q])));
-    score[out0 + pos[q]] = s;
-    cls0[out0 + pos[q]] = (int16_t)arg[q];
+    // head.py:57-63: sqrt(max_c sigmoid(cls) * sigmoid(cnt)), one rounding per operation.  sigmoid is monotone,
+    // so max_c sigmoid(x_c) = sigmoid(max_c x_c); the class is torch.max's FIRST index among equal sigmoid values.
+    const float s_best = sigmoid_f32(best[q]);
+    int a = arg[q];
+    if (second[q] != best[q] && sigmoid_f32(second[q]) == s_best) {
+      // (rare: saturated logits, or logits a few ulps apart) another, different logit rounds to the same sigmoid:
+      // walk the classes again for the first one that reaches it
+      for (int c = 0; c < a; ++c)
+        if (sigmoid_f32(E::load1(cls, (size_t)c * hw + pos[q])) == s_best) {
+          a = c;
+          break;
+        }
+    }
+    score[out0 + pos[q]] = __fsqrt_rn(__fmul_rn(s_best, sigmoid_f32(cn[q])));
+    cls0[out0 + pos[q]] = (int16_t)a;
   }
 }
 
@@ -114,7 +131,12 @@ score_points_kernel(const LevelTable lt, const int C, float* __restrict__ score,
 int launch_score_points(const LevelTable& lt, int batch, int num_classes, float* score, int16_t* cls0,
                         cudaStream_t stream) {
   const dim3 grid(lt.tile_off[lt.n_levels], batch);
-  score_points_kernel<<<grid, kTileThreads, 0, stream>>>(lt, num_classes, score, cls0);
+  if (lt.cls_dtype == B200DET_F16)
+    score_points_kernel<__half><<<grid, kTileThreads, 0, stream>>>(lt, num_classes, score, cls0);
+  else if (lt.cls_dtype == B200DET_BF16)
+    score_points_kernel<__nv_bfloat16><<<grid, kTileThreads, 0, stream>>>(lt, num_classes, score, cls0);
+  else
+    score_points_kernel<float><<<grid, kTileThreads, 0, stream>>>(lt, num_classes, score, cls0);
   return check_launch();
 }
 

@@ -258,8 +258,16 @@ __device__ __forceinline__ SelectResult select_topk_cta(const LevelTable& lt, co
     const int hw = lt.hw[l], w = lt.w[l], s = lt.stride[l];
     const float x = (float)((pos % w) * s + s / 2);
     const float y = (float)((pos / w) * s + s / 2);
-    const float* rg = lt.reg[l] + (size_t)b * 4 * hw + pos;
-    float4 d = make_float4(rg[0], rg[hw], rg[2 * hw], rg[3 * hw]);
+    const size_t r0 = (size_t)b * 4 * hw + pos;
+    float4 d;
+    if (lt.reg_dtype == B200DET_F32) {
+      const float* rg = lt.reg[l] + r0;
+      d = make_float4(rg[0], rg[hw], rg[2 * hw], rg[3 * hw]);
+    } else {                                                  // fp16 / bf16 maps of an autocast forward, read as they are
+      const void* rg = lt.reg[l];
+      d = make_float4(load_map_elem(rg, lt.reg_dtype, r0), load_map_elem(rg, lt.reg_dtype, r0 + hw),
+                      load_map_elem(rg, lt.reg_dtype, r0 + 2 * (size_t)hw), load_map_elem(rg, lt.reg_dtype, r0 + 3 * (size_t)hw));
+    }
     if (lt.reg_scale[l]) {                                    // raw regression output: ScaleExp folded in
       const float sc = *lt.reg_scale[l];
       d = make_float4(scale_exp_f32(d.x, sc), scale_exp_f32(d.y, sc), scale_exp_f32(d.z, sc), scale_exp_f32(d.w, sc));

@@ -269,7 +269,8 @@ extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* con
     return B200DET_ERR_ARG;
   if (max_gt > 0 && (!gt_boxes || !gt_labels)) return B200DET_ERR_ARG;
   if (!aligned16(gt_boxes) || !aligned16(reg_t) || !aligned16(workspace)) return B200DET_ERR_ARG;
-  if ((mode != 0 && mode != 1) || (grad_mode != 0 && grad_mode != 1)) return B200DET_ERR_UNSUPPORTED;
+  if ((mode != 0 && mode != 1) || (grad_mode != 0 && grad_mode != 1) || !fp32_levels(levels, n_levels))
+    return B200DET_ERR_UNSUPPORTED;
   const bool has_cnt = cnt_grads != nullptr;
   if (has_cnt != (cnt_loss != nullptr)) return B200DET_ERR_ARG;
   int32_t level_hw[2 * B200DET_MAX_LEVELS], strides[B200DET_MAX_LEVELS];

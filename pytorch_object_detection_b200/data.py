@@ -95,12 +95,24 @@ class DeviceCollate:
     """``collate_fn(data)`` of the reference's datasets with the batch assembled on the device.
 
     ``data`` is what a ``DataLoader`` hands over: a list of ``(img [3,h,w] f32, boxes [n,4] f32, classes [n] i64)``.
+
+    It launches CUDA work, so it must run in the MAIN process: ``DataLoader(..., num_workers=0, pin_memory=False,
+    collate_fn=DeviceCollate(...))`` (the batch it returns is already on the device).  With worker processes
+    (the reference uses ``num_workers=4``, train.py:79-86) keep decoding in the workers with a trivial
+    ``collate_fn=lambda data: data`` and call ``DeviceCollate`` on the list the loader yields; called inside a
+    worker it raises instead of failing with "Cannot re-initialize CUDA in forked subprocess".
     """
 
     def __init__(self, mean: Sequence[float], std: Sequence[float], device="cuda"):
         self.mean, self.std, self.device = list(mean), list(std), torch.device(device)
 
     def __call__(self, data):
+        import torch.utils.data as tud
+        if tud.get_worker_info() is not None:
+            raise _lib.B200DetError(
+                "DeviceCollate launches CUDA kernels and cannot run inside a DataLoader worker process: use "
+                "num_workers=0 (and pin_memory=False), or collate_fn=lambda d: d in the workers and call "
+                "DeviceCollate on the yielded list in the main process")
         imgs_list, boxes_list, classes_list = zip(*data)
         assert len(imgs_list) == len(boxes_list) == len(classes_list)          # voc.py:143
         imgs = [t if t.is_cuda else t.pin_memory().to(self.device, non_blocking=True) for t in imgs_list]

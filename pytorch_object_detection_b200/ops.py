@@ -5,7 +5,7 @@ allocates), launches on the current CUDA stream and returns without synchronisin
 no CPU implementation and no other backend: a non-CUDA tensor raises.
 
 Shapes use the reference's conventions (``model/modules/head.py``, ``model/loss.py``):
-level lists are NCHW fp32 maps, points are numbered level-major / row-major (the order
+level lists are NCHW maps (fp32; the post-process also reads fp16 / bf16 as they are), points are numbered level-major / row-major (the order
 ``reshape_cat_out`` produces), ``zip(levels, strides)`` truncation included (head.py:20).
 """
 from __future__ import annotations
@@ -68,12 +68,25 @@ def _scale_ptrs(reg_exp_scales, n: int, keep: List[Tensor]):
 
 
 _DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}       # b200det_dtype
+NATIVE_HALF_POSTPROCESS = True      # K1 / K2 read fp16 / bf16 head outputs as they are (b200det_level.dtypes)
+
+
+def _common_half(*lists, n: int):
+    """The fp16 / bf16 dtype shared by the first n maps of every given list, else None (-> fp32 up-cast)."""
+    dts = {t.dtype for lst in lists if lst is not None for t in list(lst)[:n]}
+    if len(dts) == 1:
+        dt = dts.pop()
+        if dt in (torch.float16, torch.bfloat16):
+            return dt
+    return None
 
 
 def _levels(cls: Sequence[Tensor] | None, cnt: Sequence[Tensor] | None, reg: Sequence[Tensor] | None,
-            strides: Sequence[int], reg_exp_scales=None, keep_half_cls: bool = False):
+            strides: Sequence[int], reg_exp_scales=None, keep_half_cls: bool = False, native_half: bool = False):
     """zip()-truncated level table.  Returns (ctypes array, kept tensors, P, batch, n_levels).  With
-    ``keep_half_cls`` fp16 / bf16 class maps are passed as they are (entry points that take a cls_dtype)."""
+    ``keep_half_cls`` fp16 / bf16 class maps are passed as they are (entry points that take a cls_dtype); with
+    ``native_half`` (the post-process entry points) cls + cnt maps that share a half dtype, and reg maps that do, are
+    passed as they are and declared in ``b200det_level.dtypes`` — anything else is up-cast to fp32."""
     lists = [l for l in (cls, cnt, reg) if l is not None]
     n = min([len(strides)] + [len(l) for l in lists])
     if n == 0:
@@ -82,6 +95,9 @@ def _levels(cls: Sequence[Tensor] | None, cnt: Sequence[Tensor] | None, reg: Seq
     entries = []
     batch = None
     p_total = 0
+    half_cc = _common_half(cls, cnt, n=n) if native_half and (cls is not None or cnt is not None) else None
+    half_reg = _common_half(reg, n=n) if native_half and reg is not None else None
+    dtypes = _DTYPE_CODE[half_cc or torch.float32] | (_DTYPE_CODE[half_reg or torch.float32] << 4)
     for i in range(n):
         ptrs = []
         hw = None
@@ -89,7 +105,9 @@ def _levels(cls: Sequence[Tensor] | None, cnt: Sequence[Tensor] | None, reg: Seq
             if lst is None:
                 ptrs.append(0)
                 continue
-            if keep_half_cls and ch is None and lst[i].dtype in (torch.float16, torch.bfloat16):
+            as_is = (keep_half_cls and ch is None and lst[i].dtype in (torch.float16, torch.bfloat16)) or \
+                    (half_cc is not None and ch != 4) or (half_reg is not None and ch == 4)
+            if as_is:
                 _need_cuda(lst[i], "level map")
                 t = lst[i] if lst[i].is_contiguous() else lst[i].contiguous()
             else:
@@ -114,7 +132,7 @@ def _levels(cls: Sequence[Tensor] | None, cnt: Sequence[Tensor] | None, reg: Seq
         entries = [e + (sp,) for e, sp in zip(entries, scales)]
         keep_maps, keep_scales = keep[:n_maps], keep[n_maps:]
         keep = keep_maps + keep_scales          # maps first: callers slice keep[:...] by map count
-    return _lib.make_levels(entries), keep, p_total, batch, n
+    return _lib.make_levels(entries, dtypes), keep, p_total, batch, n
 
 
 # --------------------------------------------------------------------------------------------
@@ -135,7 +153,7 @@ def postprocess(cls: Sequence[Tensor], cnt: Sequence[Tensor], reg: Sequence[Tens
     caller place it, e.g. inside a buffer that one collective gathers for several batches.
     """
     lib = _lib.load()
-    lv, keep_alive, p_total, batch, n = _levels(cls, cnt, reg, strides, reg_exp_scales)
+    lv, keep_alive, p_total, batch, n = _levels(cls, cnt, reg, strides, reg_exp_scales, native_half=True)
     dev = keep_alive[0].device
     k = min(int(max_box), p_total)
     if k > _lib.MAX_BOX:
@@ -196,7 +214,7 @@ def detection_views(packed: Tensor, batch: int, k: int):
 def score_points(cls: Sequence[Tensor], cnt: Sequence[Tensor], strides: Sequence[int]):
     """K1 alone: score [B,P] f32, class argmax [B,P] i16 (0-based)."""
     lib = _lib.load()
-    lv, keep_alive, p_total, batch, n = _levels(cls, cnt, None, strides)
+    lv, keep_alive, p_total, batch, n = _levels(cls, cnt, None, strides, native_half=True)
     dev = keep_alive[0].device
     score = torch.empty((batch, p_total), dtype=torch.float32, device=dev)
     cls0 = torch.empty((batch, p_total), dtype=torch.int16, device=dev)
@@ -212,7 +230,7 @@ def select_topk(reg: Sequence[Tensor], strides: Sequence[int], score: Tensor, cl
                 max_box: int):
     """K2 alone: (scores [B,K], classes [B,K] i32, boxes [B,K,4], points [B,K] i32, counts [B] i32)."""
     lib = _lib.load()
-    lv, keep_alive, p_total, batch, n = _levels(None, None, reg, strides)
+    lv, keep_alive, p_total, batch, n = _levels(None, None, reg, strides, native_half=True)
     dev = score.device
     k = min(int(max_box), p_total)
     assert score.shape == (batch, p_total) and score.is_contiguous() and cls0.is_contiguous()

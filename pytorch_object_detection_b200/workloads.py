@@ -40,6 +40,24 @@ def head_outputs(batch: int, num_classes: int, levels: Sequence[Tuple[int, int]]
     return cls, cnt, reg
 
 
+def saturate_logits(x, seed: int):
+    """Class logits that collapse in the fp32 sigmoid (in place on ``x[0]``; returns x): scaled so that ~15 % of
+    them exceed 16.64, where sigmoid rounds to exactly 1.0f, and — on a quarter of the points — one class copied from
+    another a few ulps higher.  The reference's argmax over sigmoid(cls) (head.py:57-62) then returns the FIRST of
+    the equal values, which an argmax over the logits would not."""
+    g = torch.Generator().manual_seed(seed)
+    for t in x[0]:
+        t.mul_(8.0).add_(45.0)
+        c = t.shape[1]
+        src, dst = c - 2, 1                                    # a later class and an earlier one
+        ulps = torch.randint(1, 4, t[:, 0].shape, generator=g)
+        bumped = (t[:, src].contiguous().view(torch.int32) + ulps.to(torch.int32)).view(torch.float32)
+        pick = torch.rand(t[:, 0].shape, generator=g) < 0.25
+        t[:, src] = torch.where(pick & (t[:, src] > 0), bumped, t[:, src])
+        t[:, dst] = torch.where(pick & (t[:, src] > 0), t[:, src].view(torch.int32).sub(ulps.to(torch.int32)).view(torch.float32), t[:, dst])
+    return x
+
+
 def gt_boxes(batch: int, max_gt: int, img_hw: Tuple[int, int], num_classes: int, seed: int):
     """GT boxes [B, M, 4] fp32 and labels [B, M] int64, padded with -1 like the
     reference's collate functions (``dataset/voc.py:164-167``, ``dataset/coco.py:157-158``)."""
@@ -85,6 +103,16 @@ def crowd_candidates(n: int, num_classes: int, seed: int, clusters: int = 50, sp
     classes = torch.where(torch.rand(n, generator=g) < 0.8, ccls[which], rnd)
     scores = torch.rand(n, generator=g) * 0.9 + 0.05
     return boxes.contiguous(), scores.contiguous(), classes.contiguous()
+
+
+def collate_case(seed: int, sizes: Sequence[Tuple[int, int]], counts: Sequence[int]):
+    """What a DataLoader hands to ``collate_fn``: a list of (img [3,h,w] f32 in [0,1), boxes [n,4] f32, classes [n] i64)."""
+    g = torch.Generator().manual_seed(seed)
+    data = []
+    for (h, w), n in zip(sizes, counts):
+        data.append((torch.rand(3, h, w, generator=g), torch.rand(n, 4, generator=g) * 50,
+                     torch.randint(1, 21, (n,), generator=g)))
+    return data
 
 
 def fingerprint(tensors: Sequence[torch.Tensor]) -> List[float]:

@@ -99,3 +99,14 @@ def assert_ap_equal(got, want, what=""):
     assert np.array_equal(np.isnan(got), np.isnan(want)), f"{what}: NaN classes differ"
     ok = ~np.isnan(want)
     assert np.all(np.abs(got[ok] - want[ok]) <= 1e-12), f"{what}: worst {np.abs(got[ok] - want[ok]).max():.3e}"
+
+
+def head_inputs_from_meta(g, levels):
+    """Regenerate a head golden's inputs from its meta row (batch, classes, seed, max_box, flavour): flavour 1 =
+    crowded boxes, 2 = saturated class logits (make_golden_r2.py)."""
+    from pytorch_object_detection_b200 import workloads as W
+    batch, ncls, seed, max_box, flavour = (int(v) for v in g["meta"][:5])
+    x = W.head_outputs(batch, ncls, levels, seed, crowded=(flavour == 1))
+    if flavour == 2:
+        x = W.saturate_logits(x, seed + 1)
+    return x, batch, max_box, [int(s) for s in g["strides"]]

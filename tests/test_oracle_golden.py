@@ -6,7 +6,7 @@ import torch
 
 from oracle import fcos_oracle as O
 from pytorch_object_detection_b200 import workloads as W
-from helpers import assert_close, assert_detections_match, assert_equal_int, load_golden
+from helpers import assert_close, assert_detections_match, assert_equal_int, head_inputs_from_meta, load_golden
 
 HEAD_CASES = {
     "head_voc_b1": (W.VOC_LEVELS, W.VOC_HW),
@@ -14,14 +14,14 @@ HEAD_CASES = {
     "head_coco_b2": (W.COCO_LEVELS, W.COCO_HW),
     "head_coco_crowded": (W.COCO_LEVELS, W.COCO_HW),
     "head_voc_k300": (W.VOC_LEVELS, W.VOC_HW),
+    "head_voc_saturated": (W.VOC_LEVELS, W.VOC_HW),      # class logits that collapse in the fp32 sigmoid (first-index rule)
 }
 
 
 def head_inputs(g, levels):
-    batch, ncls, seed, max_box, crowded = (int(v) for v in g["meta"][:5])
-    x = W.head_outputs(batch, ncls, levels, seed, crowded=bool(crowded))
+    x, batch, max_box, strides = head_inputs_from_meta(g, levels)
     assert_close(W.fingerprint(x[0] + x[1] + x[2]), g["fingerprint"], rel=1e-12, what="input fingerprint")
-    return x, batch, max_box, [int(s) for s in g["strides"]]
+    return x, batch, max_box, strides
 
 
 @pytest.mark.parametrize("name", sorted(HEAD_CASES))
