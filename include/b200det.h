@@ -193,7 +193,8 @@ int b200det_cls_loss_bwd(const b200det_level* levels, float* const* grads, int n
  *     grad_mode 1: ONE f32 device value, the upstream gradient of the batch MEAN (a loss scale) -> /B each;
  *   num_pos [B] f32: read when num_pos_ready != 0 (as b200det_assign_loss_fused / *_loss_fwd wrote it),
  *     otherwise computed first from cnt_t (> -1 marks a positive) and written;
- *   loss [B] f32 = focal sum / num_pos; mean_out [1] f32 or NULL = batch mean, added in image order.
+ *   loss [B] f32 = focal sum / num_pos; mean_out [2] f32 or NULL = {batch mean, added in image order; the upstream
+ *   gradient the gradients were written for (grad_mode 1: *grad_loss as read by this call, else 1)}.
  * workspace: b200det_cls_loss_workspace_bytes(). */
 int b200det_cls_loss_step(const b200det_level* levels, void* const* grads, int cls_dtype, int n_levels, int batch,
                           int num_classes, const int64_t* cls_t, const float* cnt_t,
@@ -207,10 +208,10 @@ int b200det_cls_loss_step(const b200det_level* levels, void* const* grads, int c
  *   + compute_reg_loss forward AND its autograd backward (loss.py:116-177)
  *   + compute_cnt_loss forward AND backward (loss.py:29-57; optional)
  *   + the `.mean()` over the batch of FCOSLoss.forward (loss.py:210-213).
- * Three launches chained by programmatic dependent launch: a per-image count of the positives
- * (num_pos scales every gradient), one streaming kernel in which the assignment never leaves shared
- * memory (targets written once and never re-read, predictions fetched at positives only), and a
- * one-CTA deterministic reduction of the loss partials.
+ * One streaming kernel (csrc/assign_stream.cuh: a fill warp writes the dense negatives with bulk copies while
+ * the other warps assign in shared memory, predictions are fetched at positives only, num_pos — which scales
+ * every gradient — travels through per-image arrival counters) and its programmatic dependent, a one-CTA
+ * deterministic reduction of the loss partials.
  *   levels[l].reg (+ .cnt when cnt_grads != NULL), h, w, stride : head outputs (read at positives)
  *   reg_grads[l] [B,4,h,w], cnt_grads[l] [B,1,h,w] (host arrays of device pointers; cnt_grads may be
  *     NULL together with cnt_loss): receive d(sum_b grad_*[b] * loss[b]) / d(map), zeros off positives
@@ -218,7 +219,9 @@ int b200det_cls_loss_step(const b200det_level* levels, void* const* grads, int c
  *     grad_mode 1: ONE f32 device value each, the upstream gradient of the batch mean (divided by B inside)
  *   cls_t / cnt_t / reg_t : the targets, as b200det_assign_targets writes them (bit-identical)
  *   box_loss / cnt_loss / num_pos [B] f32 : as b200det_box_loss_fwd / b200det_cnt_loss_fwd
- *   mean_out [2] f32 or NULL : batch means of box_loss and cnt_loss, added in image order
+ *   mean_out [4] f32 or NULL : batch means of box_loss and cnt_loss, added in image order; then the upstream
+ *     gradients of the two means the gradients were written for (grad_mode 1: *grad_box, *grad_cnt as read by THIS
+ *     call; else 1) — what its backward hands to b200det_rescale_maps as `assumed`
  *   reg_scale_grad [n_levels] f32 or NULL : d(sum_b grad_box[b] * box_loss[b]) / d(*levels[l].reg_scale)
  *     (0 for levels without reg_scale); with reg_scale set, reg_grads are gradients w.r.t. the raw x
  *   workspace : b200det_assign_loss_workspace_bytes(batch, P) bytes (tile partials); one workspace per
@@ -242,16 +245,19 @@ int b200det_scale_maps(float* const* maps, const int64_t* numel, const float* co
 
 /* The autograd backward of b200det_assign_loss_fused / b200det_cls_loss_step when their gradients were
  * written for an ASSUMED upstream gradient (grad_mode 1).  A `state` is TWO consecutive fp32 words on the
- * device: {assumed upstream gradient, 0} (the second word is a ticket the kernel uses and resets); the
- * forward entry points take a pointer to its first word.  got[s] is the upstream gradient that arrived for
- * state s.  Map i (numel[i] elements of `dtype`) belongs to state state_of[i]: if *got != assumed the map is
- * multiplied by *got / assumed in place, otherwise it is not touched; afterwards assumed = *got (unless that
- * is 0 or not finite), so that the next forward assumes the upstream gradient this backward received — under
- * torch.cuda.amp.GradScaler (train.py:127,180) that is the loss scale, constant for thousands of steps.
- * One launch.  maps / numel / state_of (n_maps <= 16) and got / state (n_states <= 4, each state listed once)
- * are HOST arrays. */
+ * device: {upstream gradient the next forward will assume, 0} (the second word is a ticket the kernel uses and
+ * resets); the forward entry points take a pointer to its first word and report the value they read in mean_out.
+ * got[s] is the upstream gradient that arrived for state s, assumed[s] the value the forward THAT IS BEING
+ * DIFFERENTIATED was given (its mean_out copy; NULL = the state's current word).  Map i (numel[i] elements of
+ * `dtype`) belongs to state state_of[i]: if *got != *assumed the map is multiplied by *got / *assumed in place,
+ * otherwise it is not touched — also when several forwards were outstanding and the shared word has moved on.
+ * Afterwards the state's word = *got (unless that is 0 or not finite), so that the next forward assumes the
+ * upstream gradient this backward received — under torch.cuda.amp.GradScaler (train.py:127,180) that is the loss
+ * scale, constant for thousands of steps.  One launch.  maps / numel / state_of (n_maps <= 16) and got / assumed /
+ * state (n_states <= 4, each state listed once; `assumed` itself may be NULL) are HOST arrays. */
 int b200det_rescale_maps(void* const* maps, const int64_t* numel, const int32_t* state_of, int dtype, int n_maps,
-                         const float* const* got, float* const* state, int n_states, void* stream);
+                         const float* const* got, const float* const* assumed, float* const* state, int n_states,
+                         void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * N4 — the datasets' collate_fn on the device (dataset/voc.py:141-173, dataset/coco.py:135-165).

@@ -54,7 +54,7 @@ PROTOTYPES = {
     "b200det_assign_loss_fused": (C.c_int, [_LV, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int,
                                             _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "b200det_scale_maps": (C.c_int, [_P, _P, _P, C.c_int, _P]),
-    "b200det_rescale_maps": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
+    "b200det_rescale_maps": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P]),
     "b200det_eval_ap_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "b200det_eval_ap": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_double, _P, C.c_size_t,
                                   _P, _P]),

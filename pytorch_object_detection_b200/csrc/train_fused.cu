@@ -39,8 +39,9 @@ constexpr int kFinalImages = 128;            // images per round at most
 __global__ void __launch_bounds__(kFinalThreads)
 finalize_losses_kernel(const int batch, const int n_tiles, const AssignTable at, const float* __restrict__ partial,
                        unsigned long long* __restrict__ counters, const float* __restrict__ grad_box, const int grad_mode,
-                       const float inv_batch, float* __restrict__ num_pos, float* __restrict__ box_loss,
-                       float* __restrict__ cnt_loss, float* __restrict__ mean_out, float* __restrict__ reg_scale_grad) {
+                       const float* __restrict__ grad_cnt, const float inv_batch, float* __restrict__ num_pos,
+                       float* __restrict__ box_loss, float* __restrict__ cnt_loss, float* __restrict__ mean_out,
+                       float* __restrict__ reg_scale_grad) {
   __shared__ float4 stage[kFinalStage];
   __shared__ float s_np[kFinalImages];
   __shared__ float2 img[kFinalImages];
@@ -93,6 +94,9 @@ finalize_losses_kernel(const int batch, const int n_tiles, const AssignTable at,
   if (tid == 0 && mean_out) {
     mean_out[0] = mb / (float)batch;
     mean_out[1] = mc / (float)batch;
+    // the upstream gradients of the two means this call's gradients were written for (grad_mode 1), for its backward
+    mean_out[2] = (grad_mode && grad_box) ? __ldcg(grad_box) : 1.f;
+    mean_out[3] = (grad_mode && grad_cnt) ? __ldcg(grad_cnt) : 1.f;
   }
   if (reg_scale_grad && tid < at.n_levels) reg_scale_grad[tid] = my_dsc;
 }
@@ -128,7 +132,8 @@ struct RescaleTable {
   long long numel[kMaxScaleMaps];
   int state_of[kMaxScaleMaps];
   const float* got[kMaxStates];
-  float* state[kMaxStates];                  // {assumed upstream gradient, ticket (as bits of an unsigned)}
+  const float* assumed[kMaxStates];          // the value THIS forward wrote its gradients for (its own copy), or NULL = *state
+  float* state[kMaxStates];                  // shared {upstream gradient the next forward will assume, ticket (an unsigned)}
 };
 
 // map[i0 + k * step] *= f for one map, 128 bits per access where the map is 16-byte aligned
@@ -195,28 +200,32 @@ __global__ void __launch_bounds__(256) rescale_maps_kernel(const RescaleTable t,
   pdl_launch_dependents();                       // (launched as a programmatic dependent: the launch latency of this
   pdl_wait();                                    //  usually empty kernel hides behind its predecessor)
   float f[kMaxStates];
-  bool any = false;
+  bool any = false, any_update = false;
 #pragma unroll
   for (int s = 0; s < kMaxStates; ++s) {
     f[s] = 1.0f;
     if (s < n_states) {
-      const float got = __ldcg(t.got[s]), assumed = __ldcg(t.state[s]);
+      const float got = __ldcg(t.got[s]), shared = __ldcg(t.state[s]);
+      const float assumed = t.assumed[s] ? __ldcg(t.assumed[s]) : shared;
       if (got != assumed) {
         f[s] = got / assumed;
         any = true;
       }
+      any_update |= got != shared;
     }
   }
-  if (!any) return;
-  const long long step = (long long)gridDim.x * 256;
-  const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
-  for (int i = 0; i < n_maps; ++i) {
-    const int so = t.state_of[i];
-    const float fi = so == 0 ? f[0] : so == 1 ? f[1] : so == 2 ? f[2] : f[3];
-    if (fi != 1.0f) rescale_map(static_cast<T*>(t.map[i]), t.numel[i], fi, i0, step);
+  if (!any && !any_update) return;
+  if (any) {
+    const long long step = (long long)gridDim.x * 256;
+    const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
+    for (int i = 0; i < n_maps; ++i) {
+      const int so = t.state_of[i];
+      const float fi = so == 0 ? f[0] : so == 1 ? f[1] : so == 2 ? f[2] : f[3];
+      if (fi != 1.0f) rescale_map(static_cast<T*>(t.map[i]), t.numel[i], fi, i0, step);
+    }
   }
-  // remember the upstream gradient that arrived (a zero / non-finite one is not a usable assumption for the
-  // next forward: its gradients could not be rescaled); only states that differed take part
+  // remember the upstream gradient that arrived for the NEXT forward (a zero / non-finite one is not a usable
+  // assumption: its gradients could not be rescaled).  The shared word changes only after every CTA has read it.
   __syncthreads();
   if (threadIdx.x < n_states) {
     const float g = __ldcg(t.got[threadIdx.x]);
@@ -335,8 +344,8 @@ extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* con
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
   const cudaError_t e2 = cudaLaunchKernelEx(&cfg, finalize_losses_kernel, batch, n_tiles, at, (const float*)a.partial,
-                                            a.counters, grad_box, grad_mode, 1.0f / (float)batch, num_pos, box_loss,
-                                            cnt_loss, mean_out, reg_scale_grad);
+                                            a.counters, grad_box, grad_mode, grad_cnt, 1.0f / (float)batch, num_pos,
+                                            box_loss, cnt_loss, mean_out, reg_scale_grad);
   if (e2 != cudaSuccess) { set_cuda_error(e2); return B200DET_ERR_CUDA; }
   return check_launch();
 }
@@ -356,8 +365,8 @@ extern "C" int b200det_scale_maps(float* const* maps, const int64_t* numel, cons
 }
 
 extern "C" int b200det_rescale_maps(void* const* maps, const int64_t* numel, const int32_t* state_of, int dtype,
-                                    int n_maps, const float* const* got, float* const* state, int n_states,
-                                    void* stream) {
+                                    int n_maps, const float* const* got, const float* const* assumed,
+                                    float* const* state, int n_states, void* stream) {
   if (!maps || !numel || !state_of || !got || !state || n_maps <= 0 || n_maps > kMaxScaleMaps || n_states <= 0 ||
       n_states > kMaxStates)
     return B200DET_ERR_ARG;
@@ -374,6 +383,7 @@ extern "C" int b200det_rescale_maps(void* const* maps, const int64_t* numel, con
     for (int r = 0; r < s; ++r)
       if (state[r] == state[s]) return B200DET_ERR_ARG;        // one ticket per state: list each state once
     t.got[s] = got[s];
+    t.assumed[s] = assumed ? assumed[s] : nullptr;
     t.state[s] = state[s];
   }
   static const bool no_pdl = getenv("B200DET_NO_PDL") && getenv("B200DET_NO_PDL")[0] == '1';

@@ -73,7 +73,8 @@ class _Upstream:
 
     The step kernels write final gradients during the forward pass, so they must know dL/d(loss) in advance.
     It starts at 1 (``total_loss.backward()``); every backward overwrites it with the value that actually
-    arrived (b200det_rescale_maps), and rescales the stored gradients only when the assumption was wrong.
+    arrived (b200det_rescale_maps), and rescales the stored gradients only when the assumption THAT forward read
+    (each forward keeps its own copy) was wrong.
     Under ``torch.cuda.amp.GradScaler`` (train.py:127,180) the upstream gradient is the loss scale, which is
     constant for thousands of steps: from the second step on the rescale pass never runs.  No host sync."""
 
@@ -105,12 +106,14 @@ class _ClsLossStep(torch.autograd.Function):
     def forward(ctx, cls_t: Tensor, mask_src, num_pos, up: _Upstream, *cls: Tensor):
         state = up.on(cls[0].device)
         loss, mean, npos, grads = ops.cls_loss_step(cls, cls_t, mask_src=mask_src, num_pos=num_pos, up_mean=state)
-        ctx.save_for_backward(state, *grads)
+        # mean[1] = the upstream gradient THIS forward read: the shared state may have moved on by the time its
+        # backward runs (two forwards outstanding, a GradScaler scale change, per-call loss weights)
+        ctx.save_for_backward(state, mean[1:2], *grads)
         ctx.up = up
         ctx.dtypes = [t.dtype for t in cls]
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(loss, npos)
-        return mean.reshape(()), loss, npos
+        return mean[0], loss, npos
 
     @staticmethod
     def backward(ctx, g_mean, *_):
@@ -119,8 +122,8 @@ class _ClsLossStep(torch.autograd.Function):
         ctx.consumed = True
         if g_mean is None:
             return (None, None, None, None, *[None] * len(ctx.dtypes))
-        state, *grads = ctx.saved_tensors
-        ops.rescale_maps_(grads, [_as_scalar(g_mean)] * len(grads), [state] * len(grads))
+        state, assumed, *grads = ctx.saved_tensors
+        ops.rescale_maps_(grads, [_as_scalar(g_mean)] * len(grads), [state] * len(grads), [assumed] * len(grads))
         ctx.up.observed = True
         return (None, None, None, None, *[g.to(dt) for g, dt in zip(grads, ctx.dtypes)])
 
@@ -227,7 +230,8 @@ def focal_loss_from_logits(preds: Tensor, targets: Tensor, gamma: float = 2.0, a
         raise NotImplementedError("the CUDA focal loss is specialised for gamma=2.0, alpha=0.25 (the reference's call)")
     p, c = preds.shape
     hot = targets > 0.5
-    assert bool((hot.sum(dim=1) <= 1).all()), "targets must be one-hot rows (or all zero)"
+    # (checked on the device, asynchronously: no host synchronisation inside the loss)
+    torch._assert_async((hot.sum(dim=1) <= 1).all(), "focal_loss_from_logits: targets must be one-hot rows (or all zero)")
     cls_t = torch.where(hot.any(dim=1), hot.float().argmax(dim=1) + 1, 0).reshape(1, p, 1)
     level = preds.t().reshape(1, c, p, 1)
     mask_src = torch.full((1, p), -1.0, dtype=torch.float32, device=preds.device)   # num_pos clamps to 1
@@ -271,10 +275,10 @@ class _FusedTargetLoss(torch.autograd.Function):
         ctx.n_reg, ctx.has_cnt = n_reg, cnt is not None
         ctx.dtypes = [t.dtype for t in maps]
         ctx.scale_shapes = [t.shape for t in scales] if scales else []
-        ctx.save_for_backward(up_box, up_cnt, *r["reg_grads"], *(r["cnt_grads"] or []),
+        mean = r["mean"]                          # [2], [3]: the upstream gradients THIS forward read (see _ClsLossStep)
+        ctx.save_for_backward(up_box, up_cnt, mean[2:3], mean[3:4], *r["reg_grads"], *(r["cnt_grads"] or []),
                               *([r["scale_grad"]] if scales else []))
         ctx.set_materialize_grads(False)
-        mean = r["mean"]
         aux = [r["cls_t"], r["cnt_t"], r["reg_t"], r["box_loss"], r["num_pos"]] + ([r["cnt_loss"]] if cnt else [])
         ctx.mark_non_differentiable(*aux)
         return (mean[0], mean[1], *aux)
@@ -284,22 +288,22 @@ class _FusedTargetLoss(torch.autograd.Function):
         if getattr(ctx, "consumed", False):
             raise RuntimeError("the fused target/loss step supports a single backward per forward")
         ctx.consumed = True
-        up_box, up_cnt, *grads = ctx.saved_tensors
+        up_box, up_cnt, read_box, read_cnt, *grads = ctx.saved_tensors
         n = ctx.n_reg
         scale_grad = grads.pop() if ctx.scale_shapes else None
-        todo, got, assumed = [], [], []
+        todo, got, state, assumed = [], [], [], []
         g_box = None if g_box is None else _as_scalar(g_box)
         g_cnt = None if g_cnt is None else _as_scalar(g_cnt)
         for i, g in enumerate(grads):
-            arrived, up = (g_box, up_box) if i < n else (g_cnt, up_cnt)
+            arrived, up, read = (g_box, up_box, read_box) if i < n else (g_cnt, up_cnt, read_cnt)
             if arrived is None:
                 grads[i] = None
             else:
-                todo.append(g); got.append(arrived); assumed.append(up)
+                todo.append(g); got.append(arrived); state.append(up); assumed.append(read)
         if scale_grad is not None and g_box is not None:
-            todo.append(scale_grad); got.append(g_box); assumed.append(up_box)
+            todo.append(scale_grad); got.append(g_box); state.append(up_box); assumed.append(read_box)
         if todo:
-            ops.rescale_maps_(todo, got, assumed)
+            ops.rescale_maps_(todo, got, state, assumed)
         out = [g if g is None else g.to(dt) for g, dt in zip(grads, ctx.dtypes)]
         if scale_grad is not None:                  # one gradient per ScaleExp.scale parameter
             out += [None if g_box is None else scale_grad[i].reshape(shp) for i, shp in enumerate(ctx.scale_shapes)]

@@ -462,7 +462,7 @@ def cls_loss_step(cls: Sequence[Tensor], cls_t: Tensor, mask_src: Tensor | None 
 
     ``num_pos`` [B] (from the fused assignment step) or ``mask_src`` (cnt_t, > -1 = positive) must be given.
     fp16 / bf16 class maps are read as they are and their gradients come back in the same type (fp32 arithmetic).
-    Returns (loss [B], mean [1], num_pos [B], grads) with grads = d(sum_b grad_loss[b] * loss[b]) / d(cls maps),
+    Returns (loss [B], mean [2] = {batch mean, upstream gradient the gradients were written for}, num_pos [B], grads) with grads = d(sum_b grad_loss[b] * loss[b]) / d(cls maps),
     grad_loss defaulting to 1/B (the gradient of the batch mean); ``up_mean`` (ONE fp32 CUDA value, exclusive
     with grad_loss) is the upstream gradient of the batch mean, e.g. a GradScaler's loss scale: grad_loss[b] = up / B."""
     lib = _lib.load()
@@ -486,7 +486,7 @@ def cls_loss_step(cls: Sequence[Tensor], cls_t: Tensor, mask_src: Tensor | None 
     ws_bytes = lib.b200det_cls_loss_workspace_bytes(batch, p_total, c)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     loss = torch.empty((batch,), dtype=torch.float32, device=dev)
-    mean = torch.empty((1,), dtype=torch.float32, device=dev)
+    mean = torch.empty((2,), dtype=torch.float32, device=dev)     # {batch mean, the upstream gradient assumed}
     grads = [torch.empty_like(x) for x in keep_alive]
     ptr = lambda x: x.data_ptr() if x is not None else None
     with torch.cuda.device(dev):
@@ -528,7 +528,8 @@ def assign_loss_fused(reg: Sequence[Tensor], cnt: Sequence[Tensor] | None, strid
     """FCOSGenTargets.forward + compute_reg_loss (+ compute_cnt_loss) forward AND backward, one kernel.
 
     Returns a dict: cls_t [B,P,1] i64, cnt_t [B,P,1], reg_t [B,P,4] (bit-identical to assign_targets),
-    box_loss / cnt_loss / num_pos [B], mean [2] (batch means of box_loss, cnt_loss), reg_grads /
+    box_loss / cnt_loss / num_pos [B], mean [4] (batch means of box_loss, cnt_loss; the upstream gradients of the
+    two means this call assumed), reg_grads /
     cnt_grads (lists shaped like the maps) = gradient of sum_b grad_*[b] * loss[b]; grad_* default to
     1/B, i.e. the gradient of the batch mean.  With ``reg_exp_scales`` (per level ONE fp32 CUDA value, the
     head's ScaleExp.scale) ``reg`` holds the raw regression outputs x, the distances are exp(x * scale),
@@ -563,7 +564,7 @@ def assign_loss_fused(reg: Sequence[Tensor], cnt: Sequence[Tensor] | None, strid
     box_loss = torch.empty((batch,), dtype=torch.float32, device=dev)
     cnt_loss = torch.empty_like(box_loss) if cnt is not None else None
     num_pos = torch.empty_like(box_loss)
-    mean = torch.empty((2,), dtype=torch.float32, device=dev) if want_mean else None
+    mean = torch.empty((4,), dtype=torch.float32, device=dev) if want_mean else None   # means + assumed upstreams
     scale_grad = torch.empty((n,), dtype=torch.float32, device=dev) if reg_exp_scales is not None else None
     ws = workspace if workspace is not None else _fused_workspace(dev, batch, p_total)
     gb = _f32c(grad_box, "grad_box").reshape(batch) if grad_box is not None else None
@@ -605,16 +606,19 @@ def scale_maps_(maps: Sequence[Tensor], factors: Sequence[Tensor]) -> None:
     _count("scale_maps")
 
 
-def rescale_maps_(maps: Sequence[Tensor], got: Sequence[Tensor], state: Sequence[Tensor]) -> None:
-    """maps[i] *= got[i] / state[i][0] where the two differ (nothing is touched where they are equal), then
+def rescale_maps_(maps: Sequence[Tensor], got: Sequence[Tensor], state: Sequence[Tensor],
+                  assumed: Sequence[Tensor] | None = None) -> None:
+    """maps[i] *= got[i] / assumed[i] where the two differ (nothing is touched where they are equal), then
     state[i][0] <- got[i]: the backward of the steps whose forward wrote gradients for an assumed upstream
-    gradient (b200det_rescale_maps, one launch).  got: 1-element, state: 2-element {assumed, ticket} fp32 CUDA
-    tensors; maps that share a state object share its got."""
+    gradient (b200det_rescale_maps, one launch).  got: 1-element, state: 2-element {next assumption, ticket},
+    assumed: 1-element fp32 CUDA tensors — the value the forward being differentiated read (its own copy: the
+    shared state may have moved on when several forwards were outstanding); None = the state's current word.
+    Maps that share a state object share its got / assumed."""
     lib = _lib.load()
     n = len(maps)
-    assert n == len(got) == len(state) and n > 0
-    states, gots, index = [], [], []
-    for t, g, a in zip(maps, got, state):
+    assert n == len(got) == len(state) and n > 0 and (assumed is None or len(assumed) == n)
+    states, gots, assumes, index = [], [], [], []
+    for i, (t, g, a) in enumerate(zip(maps, got, state)):
         _need_cuda(t, "map")
         assert t.dtype == maps[0].dtype and t.dtype in _DTYPE_CODE and t.is_contiguous()
         assert g.dtype == torch.float32 and g.numel() == 1 and g.is_cuda
@@ -627,13 +631,19 @@ def rescale_maps_(maps: Sequence[Tensor], got: Sequence[Tensor], state: Sequence
             index.append(len(states))
             states.append(a)
             gots.append(g)
+            if assumed is not None:
+                u = assumed[i]
+                assert u.dtype == torch.float32 and u.numel() == 1 and u.is_cuda
+                assumes.append(u)
     m_arr = (C.c_void_p * n)(*[t.data_ptr() for t in maps])
     n_arr = (C.c_int64 * n)(*[t.numel() for t in maps])
     i_arr = (C.c_int32 * n)(*index)
     g_arr = (C.c_void_p * len(states))(*[g.data_ptr() for g in gots])
     s_arr = (C.c_void_p * len(states))(*[a.data_ptr() for a in states])
+    a_arr = (C.c_void_p * len(states))(*[u.data_ptr() for u in assumes]) if assumed is not None else None
     with torch.cuda.device(maps[0].device):
-        rc = lib.b200det_rescale_maps(m_arr, n_arr, i_arr, _DTYPE_CODE[maps[0].dtype], n, g_arr, s_arr, len(states), _stream(maps[0]))
+        rc = lib.b200det_rescale_maps(m_arr, n_arr, i_arr, _DTYPE_CODE[maps[0].dtype], n, g_arr, a_arr, s_arr, len(states),
+                                      _stream(maps[0]))
     _lib.check(rc, "b200det_rescale_maps")
     _count("rescale_maps")
 

@@ -472,7 +472,8 @@ def test_focal_step_wide_logit_range_odd_levels_and_upstream_scale():
     a = [t.clone().to(DEV).requires_grad_(True) for t in cls]
     loss, mean, npos, grads = ops.cls_loss_step(a, cls_t.to(DEV), mask_src=cnt_t.to(DEV))
     assert_close(to_np(loss), to_np(want), rel=REL_TOL, what="per-image focal loss")
-    assert_close(float(mean), float(want.mean()), rel=REL_TOL)
+    assert_close(float(mean[0]), float(want.mean()), rel=REL_TOL)
+    assert float(mean[1]) == 1.0                                  # no upstream gradient was given: 1 assumed
     assert_equal_int(to_np(npos), np.maximum(to_np(pos.sum(dim=1)), 1))
     for gpu, ref in zip(grads, ref_in):
         assert_close(to_np(gpu), to_np(ref.grad), rel=REL_TOL, abs_=1e-9 / B, what="focal step gradient")
@@ -570,6 +571,43 @@ def test_training_step_under_a_loss_scale_assumes_the_previous_upstream_gradient
                              what=f"{type(module).__name__} gradient at loss scale {scale}")
     for up in (step._up_cls, step._up_box, step._up_cnt, plain._up_cls):
         assert up.on(torch.device(DEV)).tolist() == [512.0, 0.0]  # the zero upstream was not adopted; ticket reset
+
+
+def test_two_outstanding_forwards_and_per_call_loss_weights():
+    """Two forwards of ONE module before any backward — (lossA + lossB).backward() on the first GradScaler step,
+    gradient accumulation with per-micro-batch weights: every forward keeps its own copy of the upstream gradient it
+    assumed, so the second backward is not fooled by the state the first one has already updated.  Against CPU
+    autograd of the oracle for each input set."""
+    g, x, gt, labels, ranges, levels = train_case("train_voc_b2")
+    x2 = W.head_outputs(x[0][0].shape[0], x[0][0].shape[1], levels, seed=4242)
+    gt2, labels2 = W.gt_boxes(gt.shape[0], gt.shape[1], W.VOC_HW, x[0][0].shape[1], seed=4243)
+    sets = [(x, gt, labels), (x2, gt2, labels2)]
+
+    def reference(weights):
+        out = []
+        for (xs, g_, l_), w_ in zip(sets, weights):
+            ref = [[t.clone().requires_grad_(True) for t in part] for part in xs]
+            tgt = O.assign_targets(levels, g_, l_, W.STRIDES, ranges)
+            (O.fcos_loss(ref, tgt[:3], "giou")[3] * w_).backward()
+            out.append([t.grad.clone() for part in ref for t in part])
+        return out
+
+    for module_kind in ("fused", "plain"):
+        module = P.FCOSTargetLoss(W.STRIDES, ranges, "giou") if module_kind == "fused" else P.FCOSLoss("giou")
+        gen = P.FCOSGenTargets(W.STRIDES, ranges)
+        for weights in ((1024.0, 1024.0), (1024.0, 1024.0), (2.0, 3.0), (3.0, 2.0), (1.0, 1.0)):
+            want = reference(weights)
+            dev_sets = [([[t.to(DEV).requires_grad_(True) for t in part] for part in xs], g_.to(DEV), l_.to(DEV))
+                        for xs, g_, l_ in sets]
+            losses = []
+            for xs, g_, l_ in dev_sets:                         # BOTH forwards first
+                arg = [xs, g_, l_] if module_kind == "fused" else [xs, gen([xs, g_, l_])]
+                losses.append(module(arg)[3])
+            (losses[0] * weights[0] + losses[1] * weights[1]).backward()
+            for (xs, _, _), w_list, wt in zip(dev_sets, want, weights):
+                for got, w in zip([t for part in xs for t in part], w_list):
+                    assert_close(to_np(got.grad), to_np(w), rel=REL_TOL, abs_=1e-9 * max(wt, 1.0),
+                                 what=f"{module_kind} gradients, two outstanding forwards, weights {weights}")
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])

@@ -97,12 +97,12 @@ def test_training_step_entry_points_validate_before_launching():
     idx = (C.c_int32 * 2)(0, 1)
     got = (C.c_void_p * 2)(16, 16)
     states = (C.c_void_p * 2)(64, 128)
-    assert lib.b200det_rescale_maps(maps, numel, idx, 0, 0, got, states, 2, None) == 1        # no maps
-    assert lib.b200det_rescale_maps(maps, numel, idx, 0, 17, got, states, 2, None) == 1       # too many maps
-    assert lib.b200det_rescale_maps(maps, numel, idx, 9, 2, got, states, 2, None) == 2        # unknown dtype
-    assert lib.b200det_rescale_maps(maps, numel, (C.c_int32 * 2)(0, 2), 0, 2, got, states, 2, None) == 1   # state index
-    assert lib.b200det_rescale_maps(maps, numel, idx, 0, 2, got, (C.c_void_p * 2)(64, 64), 2, None) == 1   # duplicate state
-    assert lib.b200det_rescale_maps(maps, numel, idx, 0, 2, got, states, 5, None) == 1        # too many states
+    assert lib.b200det_rescale_maps(maps, numel, idx, 0, 0, got, None, states, 2, None) == 1        # no maps
+    assert lib.b200det_rescale_maps(maps, numel, idx, 0, 17, got, None, states, 2, None) == 1       # too many maps
+    assert lib.b200det_rescale_maps(maps, numel, idx, 9, 2, got, None, states, 2, None) == 2        # unknown dtype
+    assert lib.b200det_rescale_maps(maps, numel, (C.c_int32 * 2)(0, 2), 0, 2, got, None, states, 2, None) == 1   # state index
+    assert lib.b200det_rescale_maps(maps, numel, idx, 0, 2, got, got, (C.c_void_p * 2)(64, 64), 2, None) == 1   # duplicate state
+    assert lib.b200det_rescale_maps(maps, numel, idx, 0, 2, got, None, states, 5, None) == 1        # too many states
     assert lib.b200det_assign_loss_workspace_bytes(0, 100) == 0
     lo = (C.c_float * 1)(-1.0)
     hi = (C.c_float * 1)(64.0)
