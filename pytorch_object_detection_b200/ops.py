@@ -649,32 +649,149 @@ def rescale_maps_(maps: Sequence[Tensor], got: Sequence[Tensor], state: Sequence
 
 
 # --------------------------------------------------------------------------------------------
-# torch.library registration: the same entry points as dispatcher ops, CUDA key only
+# torch.library registration: every entry point as a dispatcher op of the ``b200det`` namespace — CUDA kernels
+# only (a CPU tensor finds no kernel and raises) plus a fake (meta) implementation that knows the output shapes, so
+# the ops can be traced / exported without running them.  Absent optional outputs come back as empty tensors.
 # --------------------------------------------------------------------------------------------
 _LIBDEF = torch.library.Library("b200det", "DEF")
-_LIBDEF.define("postprocess(Tensor[] cls, Tensor[] cnt, Tensor[] reg, int[] strides, float score_thr, "
-               "float nms_thr, int max_box, int clip_h, int clip_w) -> (Tensor, Tensor, Tensor, Tensor, Tensor)")
-_LIBDEF.define("batched_nms(Tensor boxes, Tensor scores, Tensor classes, float score_thr, float nms_thr, "
-               "int clip_h, int clip_w) -> (Tensor, Tensor, Tensor, Tensor, Tensor)")
-_LIBDEF.define("assign_targets(int[] level_hw, int[] strides, float[] limit_lo, float[] limit_hi, "
-               "Tensor gt_boxes, Tensor labels, float sample_radius) -> (Tensor, Tensor, Tensor)")
-_LIBDEF.define("clip_boxes_(Tensor(a!) boxes, int img_h, int img_w) -> Tensor(a!)")
+OP_NAMES: List[str] = []
 
 
+def _register(schema: str, impl, fake) -> None:
+    name = schema.split("(", 1)[0]
+    _LIBDEF.define(schema)
+    _LIBDEF.impl(name, impl, "CUDA")
+    torch.library.register_fake(f"b200det::{name}")(fake)
+    OP_NAMES.append(name)
+
+
+def _points(levels) -> int:
+    return sum(int(t.shape[2]) * int(t.shape[3]) for t in levels)
+
+
+def _zip_n(strides, *lists) -> int:
+    return min([len(strides)] + [len(l) for l in lists if l is not None])
+
+
+def _e(like: Tensor, shape, dtype=None) -> Tensor:
+    return like.new_empty(tuple(shape), dtype=dtype if dtype is not None else like.dtype)
+
+
+# ---- inference --------------------------------------------------------------------------------------------
 def _op_postprocess(cls, cnt, reg, strides, score_thr, nms_thr, max_box, clip_h, clip_w):
     return postprocess(cls, cnt, reg, strides, score_thr, nms_thr, max_box, (clip_h, clip_w) if clip_h > 0 else None)
+
+
+def _fake_postprocess(cls, cnt, reg, strides, score_thr, nms_thr, max_box, clip_h, clip_w):
+    n = _zip_n(strides, cls, cnt, reg)
+    b, k = cls[0].shape[0], min(int(max_box), _points(cls[:n]))
+    x = cls[0]
+    return (_e(x, (b, k), torch.float32), _e(x, (b, k), torch.int64), _e(x, (b, k, 4), torch.float32),
+            _e(x, (b, k), torch.int64), _e(x, (b,), torch.int32))
 
 
 def _op_batched_nms(boxes, scores, classes, score_thr, nms_thr, clip_h, clip_w):
     return batched_nms(boxes, scores, classes, score_thr, nms_thr, None, (clip_h, clip_w) if clip_h > 0 else None)
 
 
+def _fake_batched_nms(boxes, scores, classes, score_thr, nms_thr, clip_h, clip_w):
+    b, n = scores.shape
+    return (_e(scores, (b, n), torch.float32), _e(scores, (b, n), torch.int64), _e(scores, (b, n, 4), torch.float32),
+            _e(scores, (b, n), torch.int64), _e(scores, (b,), torch.int32))
+
+
+def _fake_score_points(cls, cnt, strides):
+    n = _zip_n(strides, cls, cnt)
+    b, p = cls[0].shape[0], _points(cls[:n])
+    return _e(cls[0], (b, p), torch.float32), _e(cls[0], (b, p), torch.int16)
+
+
+def _fake_select_topk(reg, strides, score, cls0, score_thr, max_box):
+    b, k = score.shape[0], min(int(max_box), _points(reg[:_zip_n(strides, reg)]))
+    return (_e(score, (b, k), torch.float32), _e(score, (b, k), torch.int32), _e(score, (b, k, 4), torch.float32),
+            _e(score, (b, k), torch.int32), _e(score, (b,), torch.int32))
+
+
+# ---- training targets -------------------------------------------------------------------------------------
 def _op_assign(level_hw, strides, limit_lo, limit_hi, gt_boxes, labels, sample_radius):
     hw = [(level_hw[2 * i], level_hw[2 * i + 1]) for i in range(len(strides))]
     return assign_targets(hw, strides, list(zip(limit_lo, limit_hi)), gt_boxes, labels, sample_radius)
 
 
-_LIBDEF.impl("postprocess", _op_postprocess, "CUDA")
-_LIBDEF.impl("batched_nms", _op_batched_nms, "CUDA")
-_LIBDEF.impl("assign_targets", _op_assign, "CUDA")
-_LIBDEF.impl("clip_boxes_", clip_boxes_, "CUDA")
+def _fake_assign(level_hw, strides, limit_lo, limit_hi, gt_boxes, labels, sample_radius):
+    b, p = gt_boxes.shape[0], sum(level_hw[2 * i] * level_hw[2 * i + 1] for i in range(len(strides)))
+    return (_e(gt_boxes, (b, p, 1), torch.int64), _e(gt_boxes, (b, p, 1), torch.float32),
+            _e(gt_boxes, (b, p, 4), torch.float32))
+
+
+# ---- losses -----------------------------------------------------------------------------------------------
+def _fake_loss_fwd(maps, *_):
+    b = maps[0].shape[0]
+    return _e(maps[0], (b,), torch.float32), _e(maps[0], (b,), torch.float32)
+
+
+def _fake_loss_bwd(maps, *_):
+    return [_e(t, t.shape, torch.float32) for t in maps]
+
+
+def _op_cls_loss_step(cls, cls_t, mask_src, num_pos, grad_loss, up_mean):
+    loss, mean, npos, grads = cls_loss_step(cls, cls_t, mask_src, num_pos, grad_loss, up_mean)
+    return loss, mean, npos, grads
+
+
+def _fake_cls_loss_step(cls, cls_t, mask_src, num_pos, grad_loss, up_mean):
+    b = cls[0].shape[0]
+    f = lambda shape: _e(cls[0], shape, torch.float32)                         # noqa: E731
+    return f((b,)), f((2,)), f((b,)), [_e(t, t.shape) for t in cls]            # gradients in the logits' own dtype
+
+
+def _op_assign_loss_fused(reg, cnt, strides, limit_lo, limit_hi, gt_boxes, labels, mode, sample_radius, up_box, up_cnt,
+                          reg_exp_scales):
+    r = assign_loss_fused(reg, cnt, strides, list(zip(limit_lo, limit_hi)), gt_boxes, labels, mode, sample_radius,
+                          reg_exp_scales=reg_exp_scales, up_box=up_box, up_cnt=up_cnt)
+    none = gt_boxes.new_empty((0,))
+    return (r["cls_t"], r["cnt_t"], r["reg_t"], r["box_loss"], r["cnt_loss"] if r["cnt_loss"] is not None else none,
+            r["num_pos"], r["mean"], r["reg_grads"], r["cnt_grads"] or [],
+            r["scale_grad"] if r["scale_grad"] is not None else none)
+
+
+def _fake_assign_loss_fused(reg, cnt, strides, limit_lo, limit_hi, gt_boxes, labels, mode, sample_radius, up_box, up_cnt,
+                            reg_exp_scales):
+    n = _zip_n(strides, reg, cnt)
+    b, p = reg[0].shape[0], _points(reg[:n])
+    f = lambda shape, dt=torch.float32: _e(reg[0], shape, dt)                  # noqa: E731
+    return (f((b, p, 1), torch.int64), f((b, p, 1)), f((b, p, 4)), f((b,)), f((b,) if cnt is not None else (0,)), f((b,)),
+            f((4,)), [f(t.shape) for t in reg[:n]], [f(t.shape) for t in cnt[:n]] if cnt is not None else [],
+            f((n,) if reg_exp_scales is not None else (0,)))
+
+
+def _op_rescale_maps(maps, got, state, assumed):
+    rescale_maps_(maps, got, state, assumed)
+
+
+_register("postprocess(Tensor[] cls, Tensor[] cnt, Tensor[] reg, int[] strides, float score_thr, float nms_thr, "
+          "int max_box, int clip_h, int clip_w) -> (Tensor, Tensor, Tensor, Tensor, Tensor)", _op_postprocess, _fake_postprocess)
+_register("batched_nms(Tensor boxes, Tensor scores, Tensor classes, float score_thr, float nms_thr, int clip_h, "
+          "int clip_w) -> (Tensor, Tensor, Tensor, Tensor, Tensor)", _op_batched_nms, _fake_batched_nms)
+_register("score_points(Tensor[] cls, Tensor[] cnt, int[] strides) -> (Tensor, Tensor)", score_points, _fake_score_points)
+_register("select_topk(Tensor[] reg, int[] strides, Tensor score, Tensor cls0, float score_thr, int max_box) -> "
+          "(Tensor, Tensor, Tensor, Tensor, Tensor)", select_topk, _fake_select_topk)
+_register("clip_boxes_(Tensor(a!) boxes, int img_h, int img_w) -> Tensor(a!)", clip_boxes_, lambda boxes, h, w: boxes)
+_register("assign_targets(int[] level_hw, int[] strides, float[] limit_lo, float[] limit_hi, Tensor gt_boxes, "
+          "Tensor labels, float sample_radius) -> (Tensor, Tensor, Tensor)", _op_assign, _fake_assign)
+_register("box_loss_fwd(Tensor[] reg, Tensor mask_src, Tensor reg_t, int mode) -> (Tensor, Tensor)", box_loss_fwd, _fake_loss_fwd)
+_register("box_loss_bwd(Tensor[] reg, Tensor mask_src, Tensor reg_t, int mode, Tensor grad_loss, Tensor npos) -> Tensor[]",
+          box_loss_bwd, _fake_loss_bwd)
+_register("cnt_loss_fwd(Tensor[] cnt, Tensor mask_src, Tensor cnt_t) -> (Tensor, Tensor)", cnt_loss_fwd, _fake_loss_fwd)
+_register("cnt_loss_bwd(Tensor[] cnt, Tensor mask_src, Tensor cnt_t, Tensor grad_loss, Tensor npos) -> Tensor[]",
+          cnt_loss_bwd, _fake_loss_bwd)
+_register("cls_loss_fwd(Tensor[] cls, Tensor mask_src, Tensor cls_t) -> (Tensor, Tensor)", cls_loss_fwd, _fake_loss_fwd)
+_register("cls_loss_bwd(Tensor[] cls, Tensor cls_t, Tensor grad_loss, Tensor npos) -> Tensor[]", cls_loss_bwd, _fake_loss_bwd)
+_register("cls_loss_step(Tensor[] cls, Tensor cls_t, Tensor? mask_src, Tensor? num_pos, Tensor? grad_loss, Tensor? up_mean)"
+          " -> (Tensor, Tensor, Tensor, Tensor[])", _op_cls_loss_step, _fake_cls_loss_step)
+_register("assign_loss_fused(Tensor[] reg, Tensor[]? cnt, int[] strides, float[] limit_lo, float[] limit_hi, "
+          "Tensor gt_boxes, Tensor labels, int mode, float sample_radius, Tensor? up_box, Tensor? up_cnt, "
+          "Tensor[]? reg_exp_scales) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor[], Tensor[], Tensor)",
+          _op_assign_loss_fused, _fake_assign_loss_fused)
+_register("rescale_maps_(Tensor(a!)[] maps, Tensor[] got, Tensor(b!)[] state, Tensor[]? assumed) -> ()", _op_rescale_maps,
+          lambda maps, got, state, assumed: None)

@@ -242,3 +242,41 @@ def test_sharded_oracle_equals_full_batch():
             got += O.detect(sharding.shard_levels(x, world, r), 0.05, 0.6, 1000, W.STRIDES)
         for a, b in zip(got, full):
             assert all(torch.equal(p, q) for p, q in zip(a, b))
+
+
+def test_every_dispatcher_op_has_a_cuda_kernel_and_a_fake_shape_function():
+    """The b200det torch.library namespace: CUDA-only kernels — a CPU tensor finds none — and fake
+    implementations that give the output shapes / dtypes without running anything (no GPU needed: FakeTensorMode
+    fabricates the CUDA tensors)."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from pytorch_object_detection_b200 import ops
+    assert len(ops.OP_NAMES) >= 15 and {"cls_loss_step", "assign_loss_fused", "rescale_maps_"} <= set(ops.OP_NAMES)
+    with pytest.raises(NotImplementedError):
+        torch.ops.b200det.score_points([torch.zeros(1, 2, 4, 4)], [torch.zeros(1, 1, 4, 4)], [8])
+    with pytest.raises(NotImplementedError):
+        torch.ops.b200det.box_loss_fwd([torch.zeros(1, 4, 4, 4)], torch.zeros(1, 16), torch.zeros(1, 16, 4), 1)
+    p = W.num_points(W.VOC_LEVELS)
+    with FakeTensorMode():
+        dev = "cuda"
+        x = [[torch.empty(2, c, h, w, device=dev) for h, w in W.VOC_LEVELS] for c in (20, 1, 4)]
+        s, c, b, k, n = torch.ops.b200det.postprocess(x[0], x[1], x[2], W.STRIDES[:4], 0.05, 0.6, 300, 0, 0)
+        assert s.shape == (2, 300) and c.dtype == torch.int64 and b.shape == (2, 300, 4) and n.dtype == torch.int32
+        sc, c0 = torch.ops.b200det.score_points(x[0], x[1], W.STRIDES)
+        assert sc.shape == (2, p) and c0.dtype == torch.int16
+        top = torch.ops.b200det.select_topk(x[2], W.STRIDES, sc, c0, 0.05, 100000)
+        assert top[0].shape == (2, p) and top[2].shape == (2, p, 4)
+        gt = torch.empty(2, 7, 4, device=dev)
+        lab = torch.empty(2, 7, dtype=torch.int64, device=dev)
+        t = torch.ops.b200det.assign_targets([v for hw in W.VOC_LEVELS for v in hw], W.STRIDES, [-1.0] * 5, [64.0] * 5, gt, lab, 1.5)
+        assert t[0].shape == (2, p, 1) and t[0].dtype == torch.int64 and t[2].shape == (2, p, 4)
+        loss, npos = torch.ops.b200det.box_loss_fwd(x[2], t[1], t[2], 1)
+        grads = torch.ops.b200det.box_loss_bwd(x[2], t[1], t[2], 1, loss, npos)
+        assert loss.shape == (2,) and [g.shape for g in grads] == [m.shape for m in x[2]]
+        half = [m.half() for m in x[0]]
+        l2, mean, np2, g2 = torch.ops.b200det.cls_loss_step(half, t[0], t[1], None, None, None)
+        assert mean.shape == (2,) and g2[0].dtype == torch.float16 and g2[4].shape == half[4].shape
+        r = torch.ops.b200det.assign_loss_fused(x[2], None, W.STRIDES, [-1.0] * 5, [64.0] * 5, gt, lab, 1, 1.5, None, None, None)
+        assert r[0].shape == (2, p, 1) and r[4].numel() == 0 and len(r[7]) == 5 and r[8] == [] and r[6].shape == (4,)
+        r = torch.ops.b200det.assign_loss_fused(x[2], x[1], W.STRIDES, [-1.0] * 5, [64.0] * 5, gt, lab, 0, 1.5, None, None,
+                                                [torch.empty(1, device=dev)] * 5)
+        assert r[4].shape == (2,) and len(r[8]) == 5 and r[9].shape == (5,)
