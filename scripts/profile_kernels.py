@@ -60,6 +60,9 @@ cases = {
     "batched_nms": lambda i: ops.batched_nms(cand[2], cand[0], cand[1].long(), 0.05, 0.6, cand[4]),
     "postprocess": lambda i: head.detect(sets[i % args.sets], clip_hw=W.COCO_HW),
     "assign_targets": lambda i: ops.assign_targets(W.COCO_LEVELS, W.STRIDES, W.HISFCOS_RANGES, gt, labels),
+    "assign_loss_fused": lambda i: ops.assign_loss_fused(tsets[i % 2][2], None, W.STRIDES, W.HISFCOS_RANGES, gt, labels, 1),
+    "assign_loss_fused_cnt": lambda i: ops.assign_loss_fused(tsets[i % 2][2], tsets[i % 2][1], W.STRIDES, W.HISFCOS_RANGES,
+                                                             gt, labels, 1),
     "box_loss_fwd": lambda i: ops.box_loss_fwd(tsets[i % 2][2], tgt[1], tgt[2], 1),
     "box_loss_bwd": lambda i: ops.box_loss_bwd(tsets[i % 2][2], tgt[1], tgt[2], 1, gl, npos),
     "cnt_loss_fwd": lambda i: ops.cnt_loss_fwd(tsets[i % 2][1], tgt[1], tgt[1]),
