@@ -83,7 +83,10 @@ fused_select_nms_kernel(const LevelTable lt, const float* __restrict__ score, co
   // thread keeps candidate row `tid` (raw box, class) in registers. -----------------------------------
   CandSet sel_out = set;
   sel_out.nms_box = nullptr;                                  // NMS boxes stay in registers / shared memory here
-  const SelectResult sel = select_topk_cta<REG>(lt, score, cls0, thr, max_box, sel_out, nullptr, b, sortbuf, true);
+  // (the score histogram of the select lives where the suppression mask will be: 64 KB of the 68 KB)
+  static_assert(kMaskWords * 8 >= (size_t)kHistBins * sizeof(unsigned), "histogram aliases the mask");
+  const SelectResult sel = select_topk_cta<REG>(lt, score, cls0, thr, max_box, sel_out, nullptr, b, sortbuf, true,
+                                                REG ? reinterpret_cast<unsigned*>(maskT) : nullptr, false);
   const int n = sel.count;
   const int W = (n + kNmsTile - 1) / kNmsTile;
   B200DET_STAMP(8);
@@ -146,28 +149,30 @@ fused_select_nms_kernel(const LevelTable lt, const float* __restrict__ score, co
   }
   __syncthreads();
   B200DET_STAMP(13);
-  if (tid < n) {
-    // same-class pairs: this candidate (row tid) against the later members of its class bucket;
-    // wildcard pairs (trick branch): this candidate against every wildcard box of another class.
-    // A set bit is rare, so all mask updates are shared-memory atomics (rows are not thread-private:
-    // a wildcard pair (lo, hi) is found by thread hi as well as by thread lo).
-    auto test = [&](const int other, const float4 obx, const float oar) {
-      if (suppresses(mybox, myarea, obx, oar, thr_up)) {                    // the expression is symmetric
-        const int lo = min(tid, other), hi = max(tid, other);
-        atomicOr(&maskT[col_off(hi >> 6) + lo], 1ull << (hi & 63));
-        atomicOr(&nz[lo >> 6], 1u << (hi >> 6));
-      }
+  {
+    // A set bit is rare, so all mask updates are shared-memory atomics (rows are not thread-private).
+    auto mark = [&](const int a, const int c) {
+      const int lo = min(a, c), hi = max(a, c);
+      atomicOr(&maskT[col_off(hi >> 6) + lo], 1ull << (hi & 63));
+      atomicOr(&nz[lo >> 6], 1u << (hi >> 6));
     };
-    const int bk = mycls & (kBuckets - 1);
-    for (int e = bstart[bk], e1 = bstart[bk + 1]; e < e1; ++e) {
-      const int j = order[e];
-      if (j > tid && ocls[e] == mycls) test(j, obox[e], oarea[e]);
+    // same-class pairs: thread t takes the candidate in bucket-ordered SLOT t and tests it against the later slots
+    // of its bucket — the lanes of a warp then sit in the same one or two buckets and run the same number of
+    // iterations (with one thread per candidate ROW every warp ran as long as its largest class)
+    if (tid < n) {
+      const int me = order[tid], c_me = ocls[tid];
+      const float4 b_me = obox[tid];
+      const float a_me = oarea[tid];
+      for (int e = tid + 1, e1 = bstart[(c_me & (kBuckets - 1)) + 1]; e < e1; ++e)
+        if (ocls[e] == c_me && suppresses(b_me, a_me, obox[e], oarea[e], thr_up)) mark(me, order[e]);   // symmetric
     }
-    if (trick) {
+    // wildcard pairs (trick branch): every candidate against every wildcard box of another class
+    if (trick && tid < n) {
       const int nw = s_nwild;
       for (int e = 0; e < nw; ++e) {
         const int j = wild[e];
-        if (j != tid && scls[j] != mycls) test(j, sbox[j], sarea[j]);
+        // a pair of two wildcards is found from both sides: the bit is the same
+        if (j != tid && scls[j] != mycls && suppresses(mybox, myarea, sbox[j], sarea[j], thr_up)) mark(tid, j);
       }
     }
   }
@@ -215,7 +220,7 @@ fused_select_nms_kernel(const LevelTable lt, const float* __restrict__ score, co
     const unsigned long long kw = keepw[tid >> 6];
     if ((kw >> (tid & 63)) & 1ull) {
       const int o = s_pre[tid >> 6] + __popcll(kw & ((1ull << (tid & 63)) - 1ull));
-      store_kept(set, out, o0, q0, tid, o, clip_h, clip_w, raw, set.score[o0 + tid], mycls, tid);
+      store_kept(set, out, o0, q0, tid, o, clip_h, clip_w, raw, sel.score, mycls, tid);
     }
   }
   B200DET_STAMP(11);

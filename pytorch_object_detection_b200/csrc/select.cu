@@ -26,9 +26,11 @@ namespace {
 template <bool REG>
 __global__ void __launch_bounds__(kSelThreads, 1)
 select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const int16_t* __restrict__ cls0,
-                   const float thr, const int max_box, const CandSet out, int32_t* __restrict__ cand_point) {
+                   const float thr, const int max_box, const CandSet out, int32_t* __restrict__ cand_point,
+                   const unsigned sort_bytes) {
   extern __shared__ __align__(16) unsigned long long sortbuf[];
-  select_topk_cta<REG>(lt, score, cls0, thr, max_box, out, cand_point, blockIdx.x, sortbuf);
+  unsigned* hist = REG ? reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(sortbuf) + sort_bytes) : nullptr;
+  select_topk_cta<REG>(lt, score, cls0, thr, max_box, out, cand_point, blockIdx.x, sortbuf, false, hist);
 }
 
 }  // namespace
@@ -36,15 +38,17 @@ select_topk_kernel(const LevelTable lt, const float* __restrict__ score, const i
 int launch_select_topk(const LevelTable& lt, int batch, const float* score, const int16_t* cls0, float thr,
                        int max_box, const CandSet& out, int32_t* cand_point, cudaStream_t stream) {
   const int k = max_box < lt.num_points ? max_box : lt.num_points;
-  const size_t smem = select_smem_bytes(k);
+  const unsigned sort_bytes = (unsigned)select_sort_bytes(k);
   if (lt.num_points <= kSelItems * kSelThreads) {
-    if (smem > 48 * 1024)
+    const size_t smem = select_smem_bytes(k, true);
+    if (smem > 40 * 1024)
       cudaFuncSetAttribute(select_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    select_topk_kernel<true><<<batch, kSelThreads, smem, stream>>>(lt, score, cls0, thr, max_box, out, cand_point);
+    select_topk_kernel<true><<<batch, kSelThreads, smem, stream>>>(lt, score, cls0, thr, max_box, out, cand_point, sort_bytes);
   } else {
-    if (smem > 48 * 1024)
+    const size_t smem = select_smem_bytes(k, false);
+    if (smem > 40 * 1024)
       cudaFuncSetAttribute(select_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    select_topk_kernel<false><<<batch, kSelThreads, smem, stream>>>(lt, score, cls0, thr, max_box, out, cand_point);
+    select_topk_kernel<false><<<batch, kSelThreads, smem, stream>>>(lt, score, cls0, thr, max_box, out, cand_point, sort_bytes);
   }
   return check_launch();
 }

@@ -9,6 +9,19 @@ namespace b200det {
 constexpr int kSelThreads = 1024;
 constexpr int kSelItems = 24;            // register-resident keys per thread: P <= 24576
 constexpr int kFinishMax = 512;          // undecided keys handed to the single-warp finishing phase
+// Linear score histogram of the register path: bin = trunc(score * kHistBins) — exact in fp32 (a power of two), so
+// "bin >= b" is "score >= b / kHistBins" and the bin found by the scan IS a key threshold.  16 384 bins put ~4 of
+// the 23 265 COCO points into the bin the k-th score falls in, i.e. the selection almost always fits the sort.
+constexpr int kHistBins = 16384;
+constexpr int kHistPerThread = kHistBins / kSelThreads;
+static_assert(kHistPerThread == 16, "a thread scans four uint4 of bins");
+__device__ __forceinline__ int hist_bin(uint32_t key) {
+  return min(kHistBins - 1, max(0, (int)(key_to_float(key) * (float)kHistBins)));
+}
+// Where bin b lives in shared memory: TRANSPOSED, so that a thread walking its 16 consecutive bins and the lanes of a
+// warp walking theirs touch 32 different banks (bins stored linearly: a 16-word stride between lanes, every access a
+// 16-way bank conflict — measured: scan 1.5 us, slot ranges 2.2 us instead of ~0.2 us each).
+__device__ __forceinline__ int hist_slot(int bin) { return (bin & (kHistPerThread - 1)) * kSelThreads + (bin >> 4); }
 
 __device__ __forceinline__ uint32_t load_key(const float* sc, int i, float thr) {
   const float s = sc[i];
@@ -50,13 +63,19 @@ struct SelectResult {
   // candidate row `threadIdx.x` as decoded by this thread (valid for threadIdx.x < count <= kSelThreads)
   float4 box;
   int cls;
+  float score;
 };
 
 template <bool REG>
 __device__ __forceinline__ SelectResult select_topk_cta(const LevelTable& lt, const float* __restrict__ score,
                                                 const int16_t* __restrict__ cls0, const float thr, const int max_box,
                                                 const CandSet& out, int32_t* __restrict__ cand_point, const int b,
-                                                unsigned long long* sortbuf, const bool want_max = false) {
+                                                unsigned long long* sortbuf, const bool want_max = false,
+                                                unsigned* hist = nullptr, const bool write_set = true) {
+  // `write_set` false (the fused kernel): the candidate rows stay in the registers of the threads that decoded them
+  // (SelectResult), nothing but count / mode goes to the global candidate set.
+  // `hist` (REG path only; kHistBins words of shared memory, contents irrelevant on entry): replaces the ~17
+  // block-wide bit passes of the threshold search by one pass of shared-memory atomics and one scan.
   __shared__ int s_red[64];
   __shared__ int s_scan[33];
   __shared__ uint32_t s_mm[64];
@@ -78,38 +97,150 @@ __device__ __forceinline__ SelectResult select_topk_cta(const LevelTable& lt, co
       const int i = tid + j * kSelThreads;
       sv[j] = (i < P) ? ldg_stream_f1(sc + i) : -CUDART_INF_F;
     }
+    if (hist) {                          // (while the loads are in flight) an empty histogram
+      uint4* h4 = reinterpret_cast<uint4*>(hist);
+#pragma unroll
+      for (int q = 0; q < kHistPerThread / 4; ++q) h4[tid + q * kSelThreads] = make_uint4(0u, 0u, 0u, 0u);
+      __syncthreads();
+    }
 #pragma unroll
     for (int j = 0; j < kSelItems; ++j) {
       const int i = tid + j * kSelThreads;
-      key[j] = (i < P && sv[j] >= thr) ? order_key(sv[j]) : 0u;
+      const bool valid = i < P && sv[j] >= thr;
+      key[j] = valid ? order_key(sv[j]) : 0u;
+      // one pass over the keys builds them AND counts them (every pass over 24 keys x 1024 threads costs 0.7-2 us of
+      // issue slots): bin = trunc(score * kHistBins), the same value hist_bin() recovers from the key
+      if (hist && valid) atomicAdd(&hist[hist_slot(min(kHistBins - 1, max(0, (int)(sv[j] * (float)kHistBins))))], 1u);
     }
   }
+  // ---- fast path: threshold from a histogram of the scores -------------------------------------------------
+  bool have_T = false;
+  bool radix_sorted = false;  // the selection already sits in sortbuf[kSelThreads, kSelThreads + cntT), sorted
+  uint32_t T = 0u;
+  int cntT = 0, n_valid = 0;
+  if constexpr (REG) {
+    if (hist) {
+      __syncthreads();                              // every key has been counted
+      B200DET_STAMP_NOSYNC(21);
+      // thread t owns the bins [kHistBins - 16 (t + 1), kHistBins - 16 t): thread 0 the highest scores, so that an
+      // exclusive scan over the threads counts the keys in HIGHER bins
+      const int owner = kSelThreads - 1 - tid;                  // bins [16 owner, 16 owner + 16)
+      const int lo = kHistPerThread * owner;
+      unsigned hb[kHistPerThread];
+#pragma unroll
+      for (int q = 0; q < kHistPerThread; ++q) hb[q] = hist[q * kSelThreads + owner];
+      int mine_h = 0;
+#pragma unroll
+      for (int q = 0; q < kHistPerThread; ++q) mine_h += (int)hb[q];
+      const int higher = block_exclusive_scan(mine_h, s_scan, &n_valid);
+      B200DET_STAMP_NOSYNC(22);
+      const int kk_h = min(min(max_box, P), n_valid);
+      if (kk_h > 0) {
+        if (n_valid <= next_pow2(kk_h)) {          // everything valid fits the sort: no threshold needed
+          T = 1u;                                   // (valid keys are non-zero)
+          cntT = n_valid;
+          have_T = true;
+        } else {
+          if (higher < kk_h && kk_h <= higher + mine_h) {   // the k-th score falls into one of this thread's bins
+            int c = higher, bsel = lo;
+#pragma unroll
+            for (int q = kHistPerThread - 1; q >= 0; --q) {
+              const int before = c;
+              c += (int)hb[q];
+              if (before < kk_h && kk_h <= c) {
+                bsel = lo + q;
+                s_mm[1] = (uint32_t)c;
+              }
+            }
+            s_mm[0] = (uint32_t)bsel;
+          }
+          __syncthreads();
+          const int bsel = (int)s_mm[0];
+          cntT = (int)s_mm[1];
+          __syncthreads();                          // s_mm is reused below
+          if (cntT <= next_pow2(kk_h)) {
+            // score >= bsel / kHistBins  <=>  bin >= bsel (the product is exact); bin 0 also holds scores <= 0
+            T = bsel > 0 ? order_key((float)bsel / (float)kHistBins) : 1u;
+            have_T = true;
+          }
+        }
+        // The histogram also SORTS the selection (a one-pass radix sort on the bin): every bin's slot range in
+        // descending bin order is known from the scan, selected keys take a slot of their bin with one shared-memory
+        // atomic, and the few keys that share a bin are ranked against each other (key desc, point index asc).
+        // Replaces the compaction pass and the 55-stage bitonic network when the selection fits one key per thread.
+        if (have_T && cntT <= kSelThreads) {
+          unsigned start = (unsigned)higher;
+#pragma unroll
+          for (int q = kHistPerThread - 1; q >= 0; --q) {       // counts -> first slot of the bin
+            const unsigned c = hb[q];
+            hist[q * kSelThreads + owner] = start;
+            start += c;
+          }
+          __syncthreads();
+          B200DET_STAMP_NOSYNC(23);
+          unsigned long long* tmp = sortbuf;                    // unordered inside a bin
+          unsigned long long* fin = sortbuf + kSelThreads;
+          // (four independent atomics in flight at a time: their ~100-cycle round trips overlap)
+#pragma unroll
+          for (int j0 = 0; j0 < kSelItems; j0 += 4) {
+            unsigned at[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t k_ = key[j0 + u];
+              at[u] = (k_ >= T && k_) ? atomicAdd(&hist[hist_slot(hist_bin(k_))], 1u) : 0xffffffffu;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (at[u] != 0xffffffffu)
+                tmp[at[u]] = ((unsigned long long)key[j0 + u] << 32) |
+                             (unsigned long long)(0xffffffffu - (uint32_t)(tid + (j0 + u) * kSelThreads));
+          }
+          __syncthreads();
+          B200DET_STAMP_NOSYNC(24);
+          if (tid < cntT) {
+            const unsigned long long e = tmp[tid];
+            const int bin = hist_bin((uint32_t)(e >> 32));
+            const unsigned first = bin == kHistBins - 1 ? 0u : hist[hist_slot(bin + 1)];   // = slots of all higher bins
+            const unsigned end = hist[hist_slot(bin)];
+            unsigned rank = 0;
+            for (unsigned i = first; i < end; ++i) rank += tmp[i] > e ? 1u : 0u;
+            fin[first + rank] = e;
+          }
+          radix_sorted = true;                                  // (the barrier before the decode publishes fin)
+        }
+      }
+    }
+  }
+  if (!have_T) {
   FOR_KEYS(if (kx) { ++nv; kmin = min(kmin, kx); kmax = max(kmax, kx); })
 
   // block-wide n_valid / min / max
   kmin = __reduce_min_sync(0xffffffffu, kmin);
   kmax = __reduce_max_sync(0xffffffffu, kmax);
   if (lane == 0) { s_mm[warp] = kmin; s_mm[32 + warp] = kmax; }
-  const int n_valid = block_sum(nv, s_red, phase);   // barrier inside also publishes s_mm
+  n_valid = block_sum(nv, s_red, phase);             // barrier inside also publishes s_mm
   kmin = __reduce_min_sync(0xffffffffu, s_mm[lane]);
   kmax = __reduce_max_sync(0xffffffffu, s_mm[32 + lane]);
+  }
 
   B200DET_STAMP(1);
   const int kk = min(min(max_box, P), n_valid);
   if (kk == 0) {
     if (tid == 0) { out.count[b] = 0; out.mode[b] = 0; }
-    return SelectResult{0, 0.f, make_float4(0.f, 0.f, 0.f, 0.f), -1};
+    return SelectResult{0, 0.f, make_float4(0.f, 0.f, 0.f, 0.f), -1, 0.f};
   }
 
   // ---- k-th largest key -----------------------------------------------------------------
   const int n2 = next_pow2(kk);
   const int sort_cap = n2;    // the sort below handles up to n2 keys and orders ties by point index
-  uint32_t T = kmin;          // count(key >= kmin) = n_valid
-  int cntT = n_valid;
+  if (!have_T) {
+    T = kmin;                 // count(key >= kmin) = n_valid
+    cntT = n_valid;
+  }
   const int list_cap = max(n2, 2 * kSelThreads);   // entries the dynamic shared buffer holds
   bool listed = false;        // selected entries already compacted into sortbuf[0, total)
   int total = 0;
-  if (n_valid > sort_cap) {
+  if (!have_T && n_valid > sort_cap) {
     const uint32_t diff = kmin ^ kmax;              // non-zero here unless all keys are equal
     const int top = diff ? 31 - __clz(diff) : -1;
     T = (top >= 0) ? (kmax & ~((2u << top) - 1u)) : kmax;
@@ -236,7 +367,7 @@ __device__ __forceinline__ SelectResult select_topk_cta(const LevelTable& lt, co
   }
 
   // ---- compaction (order irrelevant: sorted next) ---------------------------------------
-  if (!listed) {
+  if (!listed && !radix_sorted) {
     int mine = 0;
     FOR_KEYS(mine += (kx > T || (kx == T && ix < idx_lim)) ? 1 : 0;)
     int at = block_exclusive_scan(mine, s_scan, &total);    // kk <= total <= n2
@@ -250,6 +381,7 @@ __device__ __forceinline__ SelectResult select_topk_cta(const LevelTable& lt, co
 
   float4 my_box = make_float4(0.f, 0.f, 0.f, 0.f);
   int my_cls = -1;
+  float my_score = 0.f;
   // decode one selected point: box (head.py:29-38), class, score -> candidate row i
   auto emit = [&](const unsigned long long e, const int i) {
     const int p = (int)(0xffffffffu - (uint32_t)(e & 0xffffffffull));
@@ -279,16 +411,22 @@ __device__ __forceinline__ SelectResult select_topk_cta(const LevelTable& lt, co
     bx.w = __fadd_rn(y, d.w);
     my_box = bx;
     my_cls = (int)cls0[(size_t)b * P + p] + 1;
-    out.score[o0 + i] = key_to_float((uint32_t)(e >> 32));
-    out.cls[o0 + i] = my_cls;
-    out.src[o0 + i] = i;
-    if (cand_point) cand_point[o0 + i] = p;
-    reinterpret_cast<float4*>(out.box)[o0 + i] = bx;
+    my_score = key_to_float((uint32_t)(e >> 32));
+    if (write_set) {
+      out.score[o0 + i] = my_score;
+      out.cls[o0 + i] = my_cls;
+      out.src[o0 + i] = i;
+      if (cand_point) cand_point[o0 + i] = p;
+      reinterpret_cast<float4*>(out.box)[o0 + i] = bx;
+    }
     vmax = fmaxf(vmax, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
   };
 
   __syncthreads();
-  if (n2 <= kSelThreads) {
+  if (radix_sorted) {
+    B200DET_STAMP(5);
+    if (tid < kk) emit(sortbuf[kSelThreads + tid], tid);
+  } else if (n2 <= kSelThreads) {
     // one key per thread: shuffle network inside warps, shared memory only for distances >= 32
     unsigned long long v = (tid < total) ? sortbuf[tid] : 0ull;
     __syncthreads();
@@ -308,17 +446,21 @@ __device__ __forceinline__ SelectResult select_topk_cta(const LevelTable& lt, co
   if (out.nms_box) nms_prepare_boxes(out, b, kk, vmax, tid, kSelThreads);
   B200DET_STAMP(7);
   if (tid == 0) out.count[b] = kk;
-  return SelectResult{kk, vmax, my_box, my_cls};
+  return SelectResult{kk, vmax, my_box, my_cls, my_score};
 }
 
 
 #undef FOR_KEYS
 
 // dynamic shared memory (bytes) select_topk_cta needs for a capacity of k candidates
-inline size_t select_smem_bytes(int k) {
+inline size_t select_sort_bytes(int k) {
   int n2 = 1;
   while (n2 < k) n2 <<= 1;
   return (size_t)(n2 > 2 * kSelThreads ? n2 : 2 * kSelThreads) * sizeof(unsigned long long);
+}
+// ... plus the score histogram of the register path behind the sort buffer
+inline size_t select_smem_bytes(int k, bool with_hist) {
+  return select_sort_bytes(k) + (with_hist ? (size_t)kHistBins * sizeof(unsigned) : 0);
 }
 
 }  // namespace b200det

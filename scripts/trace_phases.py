@@ -40,3 +40,14 @@ for grp in (((0, 14),) if fused else ((0, 8), (16, 20))):
     for i in (order if fused else range(grp[0], grp[1])):
         print(f"{names[i]:32s} +{(t[i] - prev) / 1.965e3:8.2f} us   (t = {(t[i] - base) / 1.965e3:8.2f} us)")
         prev = t[i]
+
+if fused:
+    buf = (C.c_longlong * 64)()
+    fn = getattr(lib, "b200det_debug_read_trace_fused")
+    fn.argtypes = [C.c_void_p, C.c_int]
+    fn(buf, 64)
+    tt = list(buf)
+    if tt[20]:
+        labels = ["keys loaded + hist zeroed", "hist atomics", "scan", "threshold + slot ranges", "placement", "(rank + decode start ->) K2 sort stamp"]
+        pts = [tt[0], tt[20], tt[21], tt[22], tt[23], tt[24], tt[5]]
+        print("select, histogram path:", "  ".join(f"{l} +{(b - a) / 1965:.2f}" for l, a, b in zip(labels, pts, pts[1:])))
