@@ -28,6 +28,10 @@ namespace b200det {
 namespace {
 
 constexpr int kPrepThreads = 1024;
+static_assert(kPrepThreads == kHistThreads, "the score histogram is scanned by 1024 threads");
+constexpr int kPrepMaxBin = 64;        // more entries than this in one score bin: the bitonic network sorts instead
+// byte offset of the score histogram behind the keys [n2] and the source map [n] (16-byte aligned)
+__host__ __device__ inline size_t prep_hist_offset(int n, int n2) { return ((size_t)n2 * 8 + (size_t)n * 4 + 15) / 16 * 16; }
 
 // ------------------------------------------------------------------------------------------
 // prepare (stand-alone batched_nms entry)
@@ -36,17 +40,26 @@ __global__ void __launch_bounds__(kPrepThreads, 1)
 nms_prepare_kernel(const int n, const float* __restrict__ boxes, const float* __restrict__ scores,
                    const long long* __restrict__ classes, const int32_t* __restrict__ in_count,
                    const float thr, const CandSet set) {
-  extern __shared__ __align__(16) unsigned long long sortbuf[];   // [n2] keys, then [n] int source map
+  // shared memory: [n2] 64-bit keys | [n] int source map | [kHistBins] score histogram | [n] keys (radix scratch)
+  extern __shared__ __align__(16) unsigned long long sortbuf[];
   __shared__ int s_scan[33];
   __shared__ float s_fmax[32];
   const int tid = threadIdx.x;
   const int b = blockIdx.x;
   int n2 = next_pow2(n);
   int* srcmap = reinterpret_cast<int*>(sortbuf + n2);
+  unsigned* hist = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(sortbuf) + prep_hist_offset(n, n2));
+  unsigned long long* tmp = reinterpret_cast<unsigned long long*>(hist + kHistBins);
   const int n_in = in_count ? min(max(in_count[b], 0), n) : n;
   const float* sc = scores + (size_t)b * n;
 
-  // order-preserving threshold compaction: rank = index into the thresholded list (head.py:90-93)
+  {
+    uint4* h4 = reinterpret_cast<uint4*>(hist);
+#pragma unroll
+    for (int q = 0; q < kHistPerThread / 4; ++q) h4[tid + q * kPrepThreads] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  // order-preserving threshold compaction: rank = index into the thresholded list (head.py:90-93); the scores are
+  // counted into the histogram on the way (the barriers of the scan order the zero-fill before the first count)
   int m = 0;
   for (int base = 0; base < n_in; base += kPrepThreads) {
     const int i = base + tid;
@@ -55,8 +68,10 @@ nms_prepare_kernel(const int n, const float* __restrict__ boxes, const float* __
     int total;
     const int rank = m + block_exclusive_scan(ok ? 1 : 0, s_scan, &total);
     if (ok) {
-      sortbuf[rank] = ((unsigned long long)order_key(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)rank);
+      const uint32_t key = order_key(s);
+      sortbuf[rank] = ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (uint32_t)rank);
       srcmap[rank] = i;
+      atomicAdd(&hist[hist_slot(hist_bin(key))], 1u);
     }
     m += total;
   }
@@ -64,10 +79,56 @@ nms_prepare_kernel(const int n, const float* __restrict__ boxes, const float* __
     if (tid == 0) { set.count[b] = 0; set.mode[b] = 0; }
     return;
   }
-  n2 = next_pow2(m);
-  for (int i = m + tid; i < n2; i += kPrepThreads) sortbuf[i] = 0ull;
   __syncthreads();
-  bitonic_sort_desc(sortbuf, n2);   // equal scores: lower rank first = stable descending
+  // Stable descending sort (equal scores: lower rank first).  One-pass radix sort on the score bin: the scan gives every
+  // bin's slot range in descending bin order, the keys take a slot of their bin with one atomic, the few keys that share
+  // a bin are ranked against each other.  5 000 candidates: ~5 us instead of 88 us for the 8 192-key bitonic network,
+  // which stays as the fallback for overfull bins (many equal scores).
+  bool sorted = false;
+  {
+    const int owner = kPrepThreads - 1 - tid;                    // bins [16 owner, 16 owner + 16): thread 0 the highest
+    unsigned hb[kHistPerThread];
+    int mine = 0, biggest = 0;
+#pragma unroll
+    for (int q = 0; q < kHistPerThread; ++q) {
+      hb[q] = hist[q * kPrepThreads + owner];
+      mine += (int)hb[q];
+      biggest = max(biggest, (int)hb[q]);
+    }
+    int total;
+    unsigned start = (unsigned)block_exclusive_scan(mine, s_scan, &total);
+    if (block_max((float)biggest, s_fmax) <= (float)kPrepMaxBin) {
+#pragma unroll
+      for (int q = kHistPerThread - 1; q >= 0; --q) {              // counts -> first slot of the bin
+        const unsigned c = hb[q];
+        hist[q * kPrepThreads + owner] = start;
+        start += c;
+      }
+      __syncthreads();
+      for (int i = tid; i < m; i += kPrepThreads) {
+        const unsigned long long e = sortbuf[i];
+        tmp[atomicAdd(&hist[hist_slot(hist_bin((uint32_t)(e >> 32)))], 1u)] = e;
+      }
+      __syncthreads();
+      for (int i = tid; i < m; i += kPrepThreads) {
+        const unsigned long long e = tmp[i];
+        const int bin = hist_bin((uint32_t)(e >> 32));
+        const unsigned first = bin == kHistBins - 1 ? 0u : hist[hist_slot(bin + 1)];   // = slots of all higher bins
+        const unsigned end = hist[hist_slot(bin)];
+        unsigned rank = 0;
+        for (unsigned j = first; j < end; ++j) rank += tmp[j] > e ? 1u : 0u;
+        sortbuf[first + rank] = e;
+      }
+      __syncthreads();
+      sorted = true;
+    }
+  }
+  if (!sorted) {
+    n2 = next_pow2(m);
+    for (int i = m + tid; i < n2; i += kPrepThreads) sortbuf[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc(sortbuf, n2);   // equal scores: lower rank first = stable descending
+  }
 
   const size_t o0 = (size_t)b * set.cap;
   float vmax = -CUDART_INF_F;
@@ -461,7 +522,7 @@ extern "C" int b200det_batched_nms(int batch, int n, const float* boxes, const f
   nms_set_carve(workspace, batch, n, &set, &mask);
   int n2 = 1;
   while (n2 < n) n2 <<= 1;
-  const size_t smem = (size_t)n2 * 8 + (size_t)n * 4;
+  const size_t smem = prep_hist_offset(n, n2) + (size_t)kHistBins * 4 + (size_t)n * 8;
   int rc = set_smem(nms_prepare_kernel, smem);
   if (rc) return rc;
   nms_prepare_kernel<<<batch, kPrepThreads, smem, st>>>(n, boxes, scores, reinterpret_cast<const long long*>(classes),

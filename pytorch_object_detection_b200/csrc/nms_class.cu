@@ -80,20 +80,73 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
   const size_t q0 = (size_t)b * out.stride;
 
   // ---- 1. (class, rank) keys, sorted: one contiguous score-ordered segment per class -----------------------
-  float cmax = 0.f;
+  // Counting sort on the class (ids below kHistBins; the histogram and the scratch copy of the keys live where the
+  // column staging and the tile bits will be): the scan gives every class its slot range, the keys take a slot of
+  // their class with one atomic and are then ranked inside the class by their score rank.  5 000 candidates: ~5 us
+  // instead of 45 us for the 8 192-key bitonic network, which stays for class ids it cannot bin.
+  static_assert(kClassThreads == kHistThreads, "the class histogram is scanned by 1024 threads");
+  unsigned* chist = reinterpret_cast<unsigned*>(tmask);                 // [kHistBins] (tmask holds 136 x 64 x 8 bytes)
+  unsigned* tmpk = reinterpret_cast<unsigned*>(cbox_all);               // [n] (cbox_all holds 32 x 64 x 16 bytes)
+  static_assert((size_t)(kClassMaxSeg / kNmsTile) * (kClassMaxSeg / kNmsTile + 1) / 2 * kNmsTile * 8 >= (size_t)kHistBins * 4,
+                "class histogram aliases the tile bits");
+  static_assert((size_t)kClassWarps * kNmsTile * sizeof(float4) >= (size_t)B200DET_MAX_BOX * 4, "key scratch aliases the column staging");
+  {
+    uint4* h4 = reinterpret_cast<uint4*>(chist);
+#pragma unroll
+    for (int q = 0; q < kHistPerThread / 4; ++q) h4[tid + q * kClassThreads] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  float cmax = 0.f, cbig = 0.f;
   for (int i = tid; i < n2; i += kClassThreads) {
     unsigned key = 0xffffffffu;
     if (i < n) {
       const int c = set.cls[o0 + i];
       cmax = fmaxf(cmax, (c < 0 || c >= (1 << (32 - kRankBits - 1))) ? 1.f : 0.f);
+      cbig = fmaxf(cbig, (c < 0 || c >= kHistBins) ? 1.f : 0.f);
       key = ((unsigned)c << kRankBits) | (unsigned)i;
+      if (c >= 0 && c < kHistBins) atomicAdd(&chist[hist_slot(c)], 1u);
     }
     keys[i] = key;
   }
   for (int i = tid; i < kwords; i += kClassThreads) keepbits[i] = 0u;
   const bool bad_class = block_max(cmax, s_fmax) > 0.f;          // also the barrier before the sort
+  const bool unbinned = block_max(cbig, s_fmax) > 0.f;
   B200DET_STAMP(1);
-  bitonic_sort_asc_u32(keys, n2);
+  if (!unbinned) {
+    unsigned hb[kHistPerThread];                                  // thread t: classes [16 t, 16 t + 16), ascending
+    int mine = 0;
+#pragma unroll
+    for (int q = 0; q < kHistPerThread; ++q) {
+      hb[q] = chist[q * kClassThreads + tid];
+      mine += (int)hb[q];
+    }
+    int total;
+    unsigned start = (unsigned)block_exclusive_scan(mine, s_scan, &total);
+#pragma unroll
+    for (int q = 0; q < kHistPerThread; ++q) {                   // counts -> first slot of the class
+      const unsigned c = hb[q];
+      chist[q * kClassThreads + tid] = start;
+      start += c;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kClassThreads) {
+      const unsigned key = keys[i];
+      tmpk[atomicAdd(&chist[hist_slot((int)(key >> kRankBits))], 1u)] = key;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kClassThreads) {
+      const unsigned key = tmpk[i];
+      const int c = (int)(key >> kRankBits);
+      const unsigned first = c == 0 ? 0u : chist[hist_slot(c - 1)];     // = end of the classes below
+      const unsigned end = chist[hist_slot(c)];
+      unsigned rank = 0;
+      for (unsigned j = first; j < end; ++j) rank += tmpk[j] < key ? 1u : 0u;
+      keys[first + rank] = key;
+    }
+    __syncthreads();
+  } else {
+    bitonic_sort_asc_u32(keys, n2);
+  }
   B200DET_STAMP(2);
   // segment starts (order-preserving compaction) and the longest segment
   int n_seg = 0;

@@ -9,20 +9,7 @@ namespace b200det {
 constexpr int kSelThreads = 1024;
 constexpr int kSelItems = 24;            // register-resident keys per thread: P <= 24576
 constexpr int kFinishMax = 512;          // undecided keys handed to the single-warp finishing phase
-// Linear score histogram of the register path: bin = trunc(score * kHistBins) — exact in fp32 (a power of two), so
-// "bin >= b" is "score >= b / kHistBins" and the bin found by the scan IS a key threshold.  16 384 bins put ~4 of
-// the 23 265 COCO points into the bin the k-th score falls in, i.e. the selection almost always fits the sort.
-constexpr int kHistBins = 16384;
-constexpr int kHistPerThread = kHistBins / kSelThreads;
-static_assert(kHistPerThread == 16, "a thread scans four uint4 of bins");
-__device__ __forceinline__ int hist_bin(uint32_t key) {
-  return min(kHistBins - 1, max(0, (int)(key_to_float(key) * (float)kHistBins)));
-}
-// Where bin b lives in shared memory: TRANSPOSED, so that a thread walking its 16 consecutive bins and the lanes of a
-// warp walking theirs touch 32 different banks (bins stored linearly: a 16-word stride between lanes, every access a
-// 16-way bank conflict — measured: scan 1.5 us, slot ranges 2.2 us instead of ~0.2 us each).
-__device__ __forceinline__ int hist_slot(int bin) { return (bin & (kHistPerThread - 1)) * kSelThreads + (bin >> 4); }
-
+static_assert(kSelThreads == kHistThreads, "the score histogram is scanned by 1024 threads");
 __device__ __forceinline__ uint32_t load_key(const float* sc, int i, float thr) {
   const float s = sc[i];
   return (s >= thr) ? order_key(s) : 0u;
