@@ -472,13 +472,17 @@ int launch_nms(const CandSet& set, int batch, double nms_thr, int clip_h, int cl
   // Above 1000 candidates an image is in torchvision's per-class mode: nms_class_kernel finishes those images
   // (unless a class is larger than it handles) and the dense kernels below only see what is left.
   static const bool no_class = getenv("B200DET_NO_CLASS_NMS") && getenv("B200DET_NO_CLASS_NMS")[0] == '1';
+  bool class_ran = false;
   if (set.cap * 4 > kTrickMaxNumel && !no_class) {
     rc = launch_nms_class(set, batch, thr_up, zero_suppresses, clip_h, clip_w, out, stream);
     if (rc) return rc;
+    class_ran = true;
   }
-  // CTAs per image: every upper-triangle tile its own CTA up to a few waves of the machine, strided beyond
+  // CTAs per image: every upper-triangle tile its own CTA up to a few waves of the machine, strided beyond.  After the
+  // per-class kernel most images are already done and their CTAs exit at once: a small strided grid then (3 160 CTAs
+  // per image that only return cost 15 us at 8 images), which an image with an oversized class walks a little longer.
   const int tri = wblocks * (wblocks + 1) / 2;
-  const int per_image = tri < 4096 ? tri : 4096;
+  const int per_image = class_ran ? (tri < 128 ? tri : 128) : (tri < 4096 ? tri : 4096);
   if (zero_suppresses)
     nms_mask_kernel<true><<<dim3(per_image, batch), kNmsTile, 0, stream>>>(set, wblocks, cap_pad, thr_up, mask);
   else
