@@ -102,6 +102,7 @@ __device__ __forceinline__ void lane_fill_f32(float* __restrict__ p, const int n
 
 struct StreamArgs {
   int has_cnt, M, mode, grad_mode, n_tiles;
+  int arrival_polls;                  // bounded wait for num_pos (kArrivalPolls; 0 = always recount: tests)
   float inv_batch;
   const float* gt_boxes;
   const long long* gt_labels;
@@ -358,7 +359,7 @@ assign_stream_kernel(const AssignTable at, const LossMaps lm, const StreamArgs a
       if (n_pos > 0) {
         if (tid == 0) {
           unsigned long long v = 0ull;
-          for (int spin = 0; spin < kArrivalPolls; ++spin) {
+          for (int spin = 0; spin < a.arrival_polls; ++spin) {
             asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.counters + b) : "memory");
             if ((int)(v >> 32) >= n_tiles) break;
             __nanosleep(64);

@@ -313,6 +313,9 @@ extern "C" int b200det_assign_loss_fused(const b200det_level* levels, float* con
   a.mode = mode;
   a.grad_mode = grad_mode;
   a.n_tiles = n_tiles;
+  // B200DET_FORCE_RECOUNT=1 (tests): no wait for the arrival counter, every CTA with positives recounts its image
+  const bool force_recount = getenv("B200DET_FORCE_RECOUNT") && getenv("B200DET_FORCE_RECOUNT")[0] == '1';
+  a.arrival_polls = force_recount ? 0 : kArrivalPolls;
   a.inv_batch = 1.0f / (float)batch;
   a.gt_boxes = gt_boxes;
   a.gt_labels = reinterpret_cast<const long long*>(gt_labels);

@@ -573,6 +573,50 @@ def test_training_step_under_a_loss_scale_assumes_the_previous_upstream_gradient
         assert up.on(torch.device(DEV)).tolist() == [512.0, 0.0]  # the zero upstream was not adopted; ticket reset
 
 
+def test_fused_step_recount_path_many_gt_and_multi_wave_grids():
+    """The paths of the fill + patch kernel that a one-wave COCO batch of 32 never takes: (1) num_pos by the local
+    recount (forced through B200DET_FORCE_RECOUNT=1: what a CTA does when the other tiles of its image are late) must
+    give the counter's result bit for bit; (2) more ground-truth boxes than a chain thread stages in registers
+    (M > 448) and more than the 48 KB default of shared memory (M ~ 1100); (3) a grid of several waves (B = 70 at the
+    COCO size: 1 260 CTAs on 592 slots) against the separate kernels."""
+    import os
+    levels = W.VOC_LEVELS
+    for batch, m, hw, lv, seed in ((3, 40, W.VOC_HW, W.VOC_LEVELS, 71), (2, 1100, W.VOC_HW, W.VOC_LEVELS, 72),
+                                   (70, 30, W.COCO_HW, W.COCO_LEVELS, 73)):
+        gt, labels = W.gt_boxes(batch, m, hw, 20, seed=seed)
+        gt, labels = gt.to(DEV), labels.to(DEV)
+        gen = torch.Generator(device=DEV).manual_seed(seed)
+        reg = [torch.exp(torch.randn(batch, 4, h, w, device=DEV, generator=gen) + 3) for h, w in lv]
+        cnt = [torch.randn(batch, 1, h, w, device=DEV, generator=gen) for h, w in lv]
+        a = ops.assign_loss_fused(reg, cnt, W.STRIDES, W.FCOS_RANGES, gt, labels, 1)
+        os.environ["B200DET_FORCE_RECOUNT"] = "1"
+        try:
+            r = ops.assign_loss_fused(reg, cnt, W.STRIDES, W.FCOS_RANGES, gt, labels, 1)
+        finally:
+            del os.environ["B200DET_FORCE_RECOUNT"]
+        for key in ("cls_t", "cnt_t", "reg_t", "box_loss", "cnt_loss", "num_pos", "mean"):
+            assert torch.equal(a[key], r[key]), f"{key}: recount path differs (B={batch}, M={m})"
+        for x, y in zip(a["reg_grads"] + a["cnt_grads"], r["reg_grads"] + r["cnt_grads"]):
+            assert torch.equal(x, y), "gradients: recount path differs"
+        # against the separate kernels: targets bit-exact, losses and gradients of the batch means
+        t = ops.assign_targets(lv, W.STRIDES, W.FCOS_RANGES, gt, labels)
+        for key, w_ in zip(("cls_t", "cnt_t", "reg_t"), t):
+            assert torch.equal(a[key], w_), key
+        loss, npos = ops.box_loss_fwd(reg, t[1], t[2], 1)
+        assert torch.equal(npos, a["num_pos"])
+        assert_close(to_np(a["box_loss"]), to_np(loss), REL_TOL, what="box loss")
+        gl = torch.full((batch,), 1.0 / batch, device=DEV)
+        for x, y in zip(a["reg_grads"], ops.box_loss_bwd(reg, t[1], t[2], 1, gl, npos)):
+            assert_close(to_np(x), to_np(y), REL_TOL, abs_=1e-12, what="box gradients")
+    # the oracle on the many-GT case (labels, GT indices bit-exact)
+    gt, labels = W.gt_boxes(2, 1100, W.VOC_HW, 20, seed=72)
+    got = ops.assign_targets(levels, W.STRIDES, W.FCOS_RANGES, gt.to(DEV), labels.to(DEV), want_index=True)
+    want = O.assign_targets(levels, gt, labels, W.STRIDES, W.FCOS_RANGES)
+    assert_equal_int(to_np(got[0]), to_np(want[0]), what="labels, M=1100")
+    assert_equal_int(to_np(got[3]), to_np(want[3]), what="GT index, M=1100")
+    assert np.array_equal(to_np(got[2]), to_np(want[2]))
+
+
 def test_two_outstanding_forwards_and_per_call_loss_weights():
     """Two forwards of ONE module before any backward — (lossA + lossB).backward() on the first GradScaler step,
     gradient accumulation with per-micro-batch weights: every forward keeps its own copy of the upstream gradient it
