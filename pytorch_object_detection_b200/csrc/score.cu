@@ -13,16 +13,25 @@
 namespace b200det {
 namespace {
 
-constexpr int kUnroll = 8;   // independent 16-byte (fp32) / 8-byte (fp16, bf16) loads in flight per thread
 
 // CTA shape: threads x 4 points.  The kernel is ONE wave (config 2: 784 CTAs of 512 points = 5.3 per SM), but tile
 // size is not what limits it: 128-, 256- and 512-point tiles (32 / 64 / 128 threads) all measure 21.4-21.7 us.
 #ifndef B200DET_SCORE_THREADS
 #define B200DET_SCORE_THREADS 128
 #endif
+#ifndef B200DET_SCORE_PIPELINE
+#define B200DET_SCORE_PIPELINE 0      // measured: two alternating batches (loads of the next one issued before the current one
+#endif                                // is reduced) are SLOWER — 25.5 us (2 x 4 planes), 27.1 us (2 x 8), 31.7 us (2 x 6) vs 21.7 us
+#ifndef B200DET_SCORE_UNROLL
+#define B200DET_SCORE_UNROLL 8
+#endif
+#ifndef B200DET_SCORE_MINBLOCKS
+#define B200DET_SCORE_MINBLOCKS 4
+#endif
+constexpr int kUnroll = B200DET_SCORE_UNROLL;   // class planes per batch of independent 16-byte (fp32) / 8-byte (fp16, bf16) loads
 constexpr int kScoreThreads = B200DET_SCORE_THREADS;
 constexpr int kScoreTile = kScoreThreads * 4;
-constexpr int kScoreCtasPerSm = 768 / kScoreThreads;     // register budget: 85 per thread
+constexpr int kScoreCtasPerSm = B200DET_SCORE_MINBLOCKS * 128 / kScoreThreads;     // register budget
 
 // number of kScoreTile tiles before level l (levels are few: a short loop per CTA)
 __device__ __forceinline__ int score_level_of_tile(const LevelTable& lt, const int tile, int* first_tile) {
@@ -74,19 +83,44 @@ score_points_kernel(const LevelTable lt, const int C, float* __restrict__ score,
     if (p0 >= hw) return;                    // hw % 4 == 0: a 4-group is all in or all out
 #pragma unroll
     for (int q = 0; q < 4; ++q) pos[q] = p0 + q;
-    int c = 0;
-    for (; c + kUnroll <= C; c += kUnroll) {
-      float4 v[kUnroll];
+    // (B200DET_SCORE_PIPELINE: two alternating batches, the loads of the next one issued before the current one is
+    // reduced — kept as a build option because it was measured and lost, see above)
+    auto load = [&](float4* v, const int c0) {
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) v[u] = E::load4(cls, (size_t)(c + u) * hw + p0);
+      for (int u = 0; u < kUnroll; ++u) v[u] = E::load4(cls, (size_t)(c0 + u) * hw + p0);
+    };
+    auto reduce = [&](const float4* v, const int c0) {
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        upd(best[0], second[0], arg[0], v[u].x, c + u);
-        upd(best[1], second[1], arg[1], v[u].y, c + u);
-        upd(best[2], second[2], arg[2], v[u].z, c + u);
-        upd(best[3], second[3], arg[3], v[u].w, c + u);
+        upd(best[0], second[0], arg[0], v[u].x, c0 + u);
+        upd(best[1], second[1], arg[1], v[u].y, c0 + u);
+        upd(best[2], second[2], arg[2], v[u].z, c0 + u);
+        upd(best[3], second[3], arg[3], v[u].w, c0 + u);
       }
+    };
+    int c = 0;
+#if B200DET_SCORE_PIPELINE
+    float4 va[kUnroll], vb[kUnroll];
+    if (C >= kUnroll) load(va, 0);
+    while (c + kUnroll <= C) {
+      const bool more_b = c + 2 * kUnroll <= C;
+      if (more_b) load(vb, c + kUnroll);
+      reduce(va, c);
+      c += kUnroll;
+      if (!more_b) break;
+      const bool more_a = c + 2 * kUnroll <= C;
+      if (more_a) load(va, c + kUnroll);
+      reduce(vb, c);
+      c += kUnroll;
+      if (!more_a) break;
     }
+#else
+    for (; c + kUnroll <= C; c += kUnroll) {
+      float4 v[kUnroll];
+      load(v, c);
+      reduce(v, c);
+    }
+#endif
     for (; c < C; ++c) {
       const float4 v = E::load4(cls, (size_t)c * hw + p0);
       upd(best[0], second[0], arg[0], v.x, c);
