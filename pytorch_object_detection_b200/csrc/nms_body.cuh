@@ -42,6 +42,33 @@ __device__ __forceinline__ unsigned long long mask_row_bits(const float4 a, cons
   return bits;
 }
 
+// The same for the first NC (<= 32) staged columns only: the work unit of the per-class kernel's cooperative tiles
+// (a 64 x 64 tile split into 64 x 16 parts, so that a class of a few hundred boxes keeps all 32 warps of the CTA busy).
+template <bool ZERO_SUP, int NC>
+__device__ __forceinline__ unsigned mask_row_bits_part(const float4 a, const float aarea, const float4* cbox,
+                                                       const float* carea, const float thr_up) {
+  const unsigned cbase = (unsigned)__cvta_generic_to_shared(cbox);
+  unsigned bits = 0u;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    float4 c;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "r"(cbase + j * 16));
+    const bool overlap = ZERO_SUP || (fminf(a.z, c.z) > fmaxf(a.x, c.x) && fminf(a.w, c.w) > fmaxf(a.y, c.y));
+    bits |= overlap ? (1u << j) : 0u;
+  }
+  for (unsigned m = bits; m; m &= m - 1u) {
+    const int j = __ffs((int)m) - 1;
+    const float4 c = cbox[j];
+    const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, c.z), fmaxf(a.x, c.x)));
+    const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, c.w), fmaxf(a.y, c.y)));
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, carea[j]), inter));
+    if (!(ovr >= thr_up)) bits &= ~(1u << j);            // == !((double)ovr > thr), see launch_nms
+  }
+  return bits;
+}
+
 // column-block-major packed upper triangle: column block w holds the words of rows [0, (w+1)*64)
 __device__ __forceinline__ int col_off(int w) { return kNmsTile * (w * (w + 1) / 2); }   // words before column w
 

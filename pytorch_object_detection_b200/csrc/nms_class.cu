@@ -203,27 +203,39 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
     const int s0 = seg[sg], s1 = sg + 1 < n_seg ? (int)seg[sg + 1] : n;
     const int W = (s1 - s0 + kNmsTile - 1) / kNmsTile;           // 2 .. 16 blocks
     const int tiles = W * (W + 1) / 2;
-    for (int tile = warp; tile < tiles; tile += kClassWarps) {
+    // work unit = (tile, 16-column part): a class of 100-400 boxes has 3-28 tiles, too few for 32 warps
+    constexpr int kPart = 16, kParts = kNmsTile / kPart;
+    for (int i = tid; i < tiles * kNmsTile; i += kClassThreads) tmask[i] = 0ull;
+    __syncthreads();
+    for (int unit = warp; unit < tiles * kParts; unit += kClassWarps) {
+      const int tile = unit / kParts, part = unit - tile * kParts;
       int rb = 0, rem = tile;
       while (rem >= W - rb) { rem -= W - rb; ++rb; }             // row-major upper triangle
       const int cb = rb + rem;
       const int r0 = s0 + rb * kNmsTile + lane, r1 = r0 + 32;
-      const int c0 = s0 + cb * kNmsTile + lane, c1 = c0 + 32;
+      const int c0 = s0 + cb * kNmsTile + part * kPart + lane;   // (lanes 0-15 stage the part's columns)
       const float4 a0 = load_box(r0, s1), a1 = load_box(r1, s1);
-      stage_cols(load_box(c0, s1), load_box(c1, s1), c0 < s1, c1 < s1);
+      const float4 cc = lane < kPart ? load_box(c0, s1) : kNoBox;
+      __syncwarp();
+      if (lane < kPart) {
+        cbox[lane] = cc;
+        carea[lane] = c0 < s1 ? __fmul_rn(__fsub_rn(cc.z, cc.x), __fsub_rn(cc.w, cc.y)) : kNoArea;
+      }
+      __syncwarp();
       unsigned long long d0 = 0ull, d1 = 0ull;
-      if (r0 < s1) d0 = mask_row_bits<ZERO_SUP>(a0, __fmul_rn(__fsub_rn(a0.z, a0.x), __fsub_rn(a0.w, a0.y)), 0, cbox,
-                                                carea, nullptr, thr_up, false);
-      if (r1 < s1) d1 = mask_row_bits<ZERO_SUP>(a1, __fmul_rn(__fsub_rn(a1.z, a1.x), __fsub_rn(a1.w, a1.y)), 0, cbox,
-                                                carea, nullptr, thr_up, false);
+      if (r0 < s1) d0 = (unsigned long long)mask_row_bits_part<ZERO_SUP, kPart>(
+                            a0, __fmul_rn(__fsub_rn(a0.z, a0.x), __fsub_rn(a0.w, a0.y)), cbox, carea, thr_up) << (part * kPart);
+      if (r1 < s1) d1 = (unsigned long long)mask_row_bits_part<ZERO_SUP, kPart>(
+                            a1, __fmul_rn(__fsub_rn(a1.z, a1.x), __fsub_rn(a1.w, a1.y)), cbox, carea, thr_up) << (part * kPart);
       if (cb == rb) {                                            // diagonal tile: only later boxes (j > row)
         d0 &= ~((2ull << lane) - 1ull);
         d1 &= ~((2ull << (lane + 32)) - 1ull);
       }
-      tmask[(size_t)tile * kNmsTile + lane] = d0;
-      tmask[(size_t)tile * kNmsTile + lane + 32] = d1;
+      if (d0) atomicOr(&tmask[(size_t)tile * kNmsTile + lane], d0);
+      if (d1) atomicOr(&tmask[(size_t)tile * kNmsTile + lane + 32], d1);
     }
     __syncthreads();
+    if (k == rank) { B200DET_STAMP_NOSYNC(10); B200DET_NOTE_IF(blockIdx.x == 0 && blockIdx.y == 0, 12, W); B200DET_NOTE_IF(blockIdx.x == 0 && blockIdx.y == 0, 13, n_big); }
     if (warp == 0) {
       unsigned long long myrem = 0ull;                           // lane w: removed bits of the class's block w
       int tile = 0;
@@ -244,7 +256,9 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
       }
     }
     __syncthreads();
+    if (k == rank) B200DET_STAMP_NOSYNC(11);
   }
+  B200DET_STAMP_NOSYNC(14);
 
   // 2b. classes of at most 64 boxes: one warp each, a single diagonal tile, nothing stored
   for (int sg = rank * kClassWarps + warp; sg < n_seg; sg += kClassCluster * kClassWarps) {

@@ -16,3 +16,5 @@ fn(buf, 64)
 t = list(buf)
 names = ["keys", "sort", "segments", "class warps", "write"]
 print(" ".join(f"{n} +{(t[i + 1] - t[i]) / 1965:.1f}us" for i, n in enumerate(names)), "segments", t[8])
+if t[10]:
+    print(f"first big class of CTA 0: tiles evaluated +{(t[10] - t[3]) / 1965:.1f}us greedy +{(t[11] - t[10]) / 1965:.1f}us (W = {t[12]} blocks, {t[13]} big classes in the image); all big classes done +{(t[14] - t[3]) / 1965:.1f}us, small classes +{(t[4] - t[14]) / 1965:.1f}us")
