@@ -617,6 +617,85 @@ def test_fused_step_recount_path_many_gt_and_multi_wave_grids():
     assert np.array_equal(to_np(got[2]), to_np(want[2]))
 
 
+def test_fill_and_patch_kernel_stays_inside_its_buffers():
+    """compute-sanitizer is closed on this pool, so the bulk-copy fill is checked with guard bands: every output of
+    b200det_assign_targets / b200det_assign_loss_fused is placed (through the C ABI) in the middle of a larger buffer
+    filled with a canary, at the odd point counts that make the fill's scalar heads / tails non-trivial (P odd, a
+    13 x 21 level, images whose first point is not 16-byte aligned); the canaries must survive and the payload must equal
+    the normal call's."""
+    import ctypes as C
+    lib = _lib.load()
+    GUARD = 1024                                         # bytes on either side
+    levels = [(13, 21), (7, 11), (5, 5), (3, 3), (1, 1)]            # P = 273 + 77 + 25 + 9 + 1 = 385 (odd)
+    strides = W.STRIDES
+    ranges = [[-1, 64], [64, 128], [128, 256], [256, 512], [512, 999999]]
+    hw_img = (13 * 8, 21 * 8)
+    batch, m = 3, 9
+    p_total = sum(h * w for h, w in levels)
+    gt, labels = W.gt_boxes(batch, m, hw_img, 20, seed=81)
+    gt, labels = gt.to(DEV), labels.to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(81)
+    reg = [torch.exp(torch.randn(batch, 4, h, w, device=DEV, generator=gen) + 2) for h, w in levels]
+    cnt = [torch.randn(batch, 1, h, w, device=DEV, generator=gen) for h, w in levels]
+    want = ops.assign_loss_fused(reg, cnt, strides, ranges, gt, labels, 1)
+    want_t = ops.assign_targets(levels, strides, ranges, gt, labels, want_index=True)
+
+    def guarded(nbytes):
+        buf = torch.full((nbytes + 2 * GUARD,), 0xA5, dtype=torch.uint8, device=DEV)
+        return buf, buf.data_ptr() + GUARD
+
+    def check(buf, nbytes, what):
+        assert bool((buf[:GUARD] == 0xA5).all()) and bool((buf[GUARD + nbytes:] == 0xA5).all()), f"{what}: write outside the buffer"
+        return buf[GUARD:GUARD + nbytes]
+
+    n = len(levels)
+    hw_arr = (C.c_int32 * (2 * n))(*[v for hw in levels for v in hw])
+    st_arr = (C.c_int32 * n)(*strides)
+    lo_arr = (C.c_float * n)(*[float(r[0]) for r in ranges])
+    hi_arr = (C.c_float * n)(*[float(r[1]) for r in ranges])
+    ra_arr = (C.c_float * n)(*[float(s_ * 1.5) for s_ in strides])
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    sizes = {"cls_t": batch * p_total * 8, "cnt_t": batch * p_total * 4, "reg_t": batch * p_total * 16, "idx": batch * p_total * 4}
+    # ---- assign only -----------------------------------------------------------------------------------------
+    bufs = {k: guarded(v) for k, v in sizes.items()}
+    rc = lib.b200det_assign_targets(hw_arr, st_arr, lo_arr, hi_arr, ra_arr, n, batch, m, gt.data_ptr(), labels.data_ptr(),
+                                    bufs["cls_t"][1], bufs["cnt_t"][1], bufs["reg_t"][1], bufs["idx"][1], stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    for key, w_, dt in (("cls_t", want_t[0], torch.int64), ("cnt_t", want_t[1], torch.float32),
+                        ("reg_t", want_t[2], torch.float32), ("idx", want_t[3], torch.int32)):
+        got = check(bufs[key][0], sizes[key], key).view(dt)
+        assert torch.equal(got, w_.reshape(-1)), key
+    # ---- fused: targets + gradients -------------------------------------------------------------------------------
+    bufs = {k: guarded(v) for k, v in sizes.items() if k != "idx"}
+    greg = [guarded(t.numel() * 4) for t in reg]
+    gcnt = [guarded(t.numel() * 4) for t in cnt]
+    small = {k: guarded(batch * 4) for k in ("box_loss", "cnt_loss", "num_pos")}
+    mean = guarded(16)
+    lv = _lib.make_levels([(0, c_.data_ptr(), r_.data_ptr(), h, w, s_) for c_, r_, (h, w), s_ in zip(cnt, reg, levels, strides)])
+    ws_bytes = lib.b200det_assign_loss_workspace_bytes(batch, p_total)
+    ws = torch.zeros(ws_bytes + 2 * GUARD, dtype=torch.uint8, device=DEV)
+    ws[:GUARD] = 0xA5
+    ws[GUARD + ws_bytes:] = 0xA5
+    rc = lib.b200det_assign_loss_fused(lv, (C.c_void_p * n)(*[g_[1] for g_ in greg]), (C.c_void_p * n)(*[g_[1] for g_ in gcnt]), n,
+                                       lo_arr, hi_arr, ra_arr, batch, m, gt.data_ptr(), labels.data_ptr(), 1, None, None, 0,
+                                       bufs["cls_t"][1], bufs["cnt_t"][1], bufs["reg_t"][1], small["box_loss"][1],
+                                       small["cnt_loss"][1], small["num_pos"][1], mean[1], None, ws.data_ptr() + GUARD, ws_bytes,
+                                       stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert bool((ws[:GUARD] == 0xA5).all()) and bool((ws[GUARD + ws_bytes:] == 0xA5).all()), "workspace overrun"
+    for key, dt in (("cls_t", torch.int64), ("cnt_t", torch.float32), ("reg_t", torch.float32)):
+        assert torch.equal(check(bufs[key][0], sizes[key], key).view(dt), want[key].reshape(-1)), key
+    for (buf, _), w_ in zip(greg, want["reg_grads"]):
+        assert torch.equal(check(buf, w_.numel() * 4, "reg grad").view(torch.float32), w_.reshape(-1))
+    for (buf, _), w_ in zip(gcnt, want["cnt_grads"]):
+        assert torch.equal(check(buf, w_.numel() * 4, "cnt grad").view(torch.float32), w_.reshape(-1))
+    for key in ("box_loss", "cnt_loss", "num_pos"):
+        assert torch.equal(check(small[key][0], batch * 4, key).view(torch.float32), want[key])
+    assert torch.equal(check(mean[0], 16, "mean").view(torch.float32), want["mean"])
+
+
 def test_two_outstanding_forwards_and_per_call_loss_weights():
     """Two forwards of ONE module before any backward — (lossA + lossB).backward() on the first GradScaler step,
     gradient accumulation with per-micro-batch weights: every forward keeps its own copy of the upstream gradient it
