@@ -87,7 +87,7 @@ __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int s
 
 // Resolve one 64-row block given the already-removed bits `cur` and the block's diagonal words
 // held lane-per-row (d0: row lane, d1: row lane+32).  If no still-alive row suppresses another
-// still-alive row (one warp OR-reduction) all alive rows are kept at once; otherwise the kept rows
+// still-alive row (one warp OR-reduction) all alive rows are kept at once; otherwise the 64 rows
 // are walked serially out of registers (shuffles), the greedy rule of torchvision's nms kernel.
 __device__ __forceinline__ unsigned long long resolve_block(const unsigned long long cur, const unsigned long long valid,
                                                             const unsigned long long d0, const unsigned long long d1,
@@ -95,16 +95,16 @@ __device__ __forceinline__ unsigned long long resolve_block(const unsigned long 
   const bool a0 = !((cur >> lane) & 1ull), a1 = !((cur >> (lane + 32)) & 1ull);
   const unsigned long long S = warp_or64((a0 ? d0 : 0ull) | (a1 ? d1 : 0ull));
   if (((S & ~cur) & valid) == 0ull) return ~cur & valid;
-  // Walk the KEPT rows only: the next kept row is the lowest row that is neither removed nor visited (every row
-  // below it is decided), so a block of a dense cluster costs as many steps as it keeps boxes, not 64.
+  // (Walking only the kept rows — next = lowest row neither removed nor visited — was measured and is SLOWER: its
+  // shuffle depends on the previous step, ~40 cycles each, while here the 64 row fetches are independent of the
+  // chain and pipeline; 1 000 crowded candidates x 16 images: 80.6 vs 68.6 us.)
   unsigned long long c = cur, keep = 0ull;
-  unsigned long long todo = ~c & valid;
-  while (todo) {
-    const int i = __ffsll((long long)todo) - 1;
+#pragma unroll 8
+  for (int i = 0; i < kNmsTile; ++i) {
     const unsigned long long di = shfl64(i < 32 ? d0 : d1, i & 31);
-    keep |= 1ull << i;
-    c |= di;
-    todo = ~c & valid & ~((2ull << i) - 1ull);
+    const bool alive = ((valid >> i) & 1ull) && !((c >> i) & 1ull);
+    keep |= alive ? (1ull << i) : 0ull;
+    c |= alive ? di : 0ull;
   }
   return keep;
 }

@@ -53,7 +53,12 @@ crowd = [W.crowd_candidates(5000, 80, seed=400 + i) for i in range(8)]
 cb = torch.stack([c[0] for c in crowd]).to(dev)
 cs = torch.stack([c[1] for c in crowd]).to(dev)
 cc = torch.stack([c[2] for c in crowd]).to(dev)
+crowd1k = [W.crowd_candidates(1000, 80, seed=4100 + i) for i in range(16)]
+kb = torch.stack([c[0] for c in crowd1k]).to(dev)
+ks = torch.stack([c[1] for c in crowd1k]).to(dev)
+kc = torch.stack([c[2] for c in crowd1k]).to(dev)
 cases = {
+    "nms_crowd1000_b16": lambda i: ops.batched_nms(kb, ks, kc, 0.05, 0.6),
     "nms_crowd5000_b8": lambda i: ops.batched_nms(cb, cs, cc, 0.05, 0.6),
     "score_points": lambda i: ops.score_points(sets[i % args.sets][0], sets[i % args.sets][1], W.STRIDES),
     "select_topk": lambda i: ops.select_topk(sets[0][2], W.STRIDES, score, cls0, 0.05, 1000),
