@@ -22,7 +22,7 @@
 // low word once all tiles of the image have arrived.  The grid is image-major, so these are neighbouring CTAs that
 // run the same schedule; the wait is BOUNDED (a few microseconds), after which the CTA recounts the image's
 // positives itself (all boxes x levels x window points into a bitmap in shared memory) — no unbounded spinning, no
-// co-residency assumption, no second kernel.
+// co-residency assumption, no count kernel in front.
 // finalize_losses_kernel (train_fused.cu; one CTA, a programmatic dependent: it is resident before this grid ends) adds
 // the tile partials in tile order and the per-image losses in image order (deterministic), publishes num_pos[] and
 // the batch means and clears the counters for the next call.  (Folding it into this kernel — a ticket, the last CTA
