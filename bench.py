@@ -15,8 +15,8 @@ consecutive passes (16 replays of a CUDA graph of 8 passes over 8 rotating input
                 the call of head.py:94) on this host, full batch of 16
   config3       BASELINE config 3: target assignment + GIoU fwd/bwd, B=32, M<=100: us/batch, roofline, cpu_baseline
   config4       dense crowd: 5 000-candidate NMS and 300-GT assignment (time only: latency-bound)
-  config5       B=256 STRONG-scaled over the ranks: post-process + FCOSTargetLoss step + detection gather + loss
-                all-reduce
+  config5       B=256 STRONG-scaled over the ranks: post-process + FCOSTargetLoss step + one gather of the detections
+                and the loss sums
   reference_eager_b200   the reference's torch ops + torchvision CUDA NMS run eagerly on this GPU (informative)
 With --impl reference only the CPU arm runs (rank 0), without importing the product package.
 Multi-GPU (torchrun): batch sharded by rank (weak scaling, 16 images per GPU per pass); the packed detections of
@@ -714,8 +714,8 @@ def train_legs(B, ops, dev, peak, sampler):
 def strong_scaling_leg(B, ops, sharding, dist, dev, rank, world, barrier, max_over_ranks, sampler):
     """BASELINE config 5: a batch of 256 split contiguously over the ranks (256/128/64/32 images per GPU).  Per step
     every rank runs the post-process of its shard and one FCOSTargetLoss training step (targets + focal + centerness +
-    GIoU losses + all gradients); the detections are gathered (one NCCL all_gather of the packed buffer) and the
-    per-image losses reduced to the batch means (ONE all_reduce, loss.py:210-213 / train.py:185-186)."""
+    GIoU losses + all gradients); the packed detections and the rank's share of the batch-mean losses (loss.py:210-213)
+    travel to rank 0 in ONE buffer per step (train.py:185-186 gathers its loss the same way)."""
     if STRONG_BATCH % world:
         return None
     lo, hi = sharding.shard_bounds(STRONG_BATCH, world, rank)
@@ -733,9 +733,27 @@ def strong_scaling_leg(B, ops, sharding, dist, dev, rank, world, barrier, max_ov
     # per-image select/NMS CTAs of the others, as in the weak-scaling loop); their packed outputs share ONE buffer
     spans = [(i, min(i + BATCH, nb)) for i in range(0, nb, BATCH)]
     sizes = [ops.packed_nbytes(hi_ - lo_, k_out) for lo_, hi_ in spans]
-    pk = torch.empty((sum(sizes),), dtype=torch.uint8, device=dev)
-    full = torch.empty((world, pk.numel()), dtype=torch.uint8, device=dev) if world > 1 else None
+    # ONE buffer per rank for everything that travels: the packed detections of its micro-batches and, in a 256-byte
+    # tail, the sums of its per-image losses (cls, cnt, reg) — so the step's only communication is one gather
+    pk_all = torch.zeros((sum(sizes) + 256,), dtype=torch.uint8, device=dev)
+    pk = pk_all[:sum(sizes)]
+    loss_tail = pk_all[sum(sizes):sum(sizes) + 12].view(torch.float32)
+    full = torch.empty((world, pk_all.numel()), dtype=torch.uint8, device=dev) if world > 1 else None
     offs = [sum(sizes[:i]) for i in range(len(sizes))]
+    # the gather: to rank 0 (where an evaluation / the logging lives, train.py:185-186) by peer-memory pushes on the
+    # copy engines + a device barrier (sharding.PeerGather), NCCL all_gather where symmetric memory is unavailable
+    peer = None
+    if dist is not None and os.environ.get("B200DET_BENCH_GATHER", "peer_root").startswith("peer"):
+        try:
+            peer = sharding.PeerGather(pk_all.numel(), 2, dev)
+        except Exception as e:                              # noqa: BLE001
+            print(f"[bench] rank {rank}: config 5 falls back to NCCL ({type(e).__name__}: {e})", file=sys.stderr)
+    if dist is not None:
+        flag = torch.tensor([1.0 if peer is not None else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag[0]) == 0.0:
+            peer = None
+    gathers = [0]
     x_mb = [[[t.detach()[lo_:hi_] for t in part] for part in (cls, cnt, reg)] for lo_, hi_ in spans]
     post_streams = [torch.cuda.Stream(device=dev) for _ in range(min(8, len(spans)))]
     side = torch.cuda.Stream(device=dev)
@@ -754,6 +772,8 @@ def strong_scaling_leg(B, ops, sharding, dist, dev, rank, world, barrier, max_ov
         for t in cls + cnt + reg:
             t.grad = None
         step([(cls, cnt, reg), gt, labels])[3].backward()
+        per = step.per_image                                # this rank's share of the batch-mean losses (loss.py:210-213)
+        loss_tail.copy_(torch.stack([per[k].sum() for k in ("cls", "cnt", "reg")]) / STRONG_BATCH)
 
     def both(_i=0):                                         # the two halves are independent: fork / join
         cur = torch.cuda.current_stream()
@@ -764,17 +784,14 @@ def strong_scaling_leg(B, ops, sharding, dist, dev, rank, world, barrier, max_ov
         cur.wait_stream(side)
 
     def collectives(which):
-        out = None
-        if dist is not None:
-            if which in ("post", "both"):
-                dist.all_gather_into_tensor(full, pk)
-        if which in ("train", "both"):
-            per = step.per_image
-            if dist is not None:
-                out = sharding.reduce_image_losses([per["cls"], per["cnt"], per["reg"]], STRONG_BATCH)
-            else:
-                out = [per[k].sum() / STRONG_BATCH for k in ("cls", "cnt", "reg")]
-        return out
+        """One gather per step: detections and loss sums in one buffer.  Returns the receiver's [world, bytes] view."""
+        if dist is None:
+            return pk_all[None]
+        if peer is not None:
+            gathers[0] += 1
+            return peer.gather(gathers[0] % 2, pk_all, root=0)
+        dist.all_gather_into_tensor(full, pk_all)
+        return full
 
     def timed(fn, which, iters=20, warm=3):
         for _ in range(2):
@@ -784,7 +801,7 @@ def strong_scaling_leg(B, ops, sharding, dist, dev, rank, world, barrier, max_ov
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 fn()
-            run, how = g.replay, "CUDA graph + eager NCCL"
+            run, how = g.replay, "CUDA graph of the compute + eager gather"
         except Exception:                                   # noqa: BLE001
             torch.cuda.synchronize()
             run, how = fn, "eager"
@@ -804,14 +821,20 @@ def strong_scaling_leg(B, ops, sharding, dist, dev, rank, world, barrier, max_ov
 
     ms_post, how, _ = timed(post, "post")
     ms_train, _, _ = timed(train, "train")
-    ms_both, _, losses = timed(both, "both")
+    ms_both, _, view = timed(both, "both")
+    torch.cuda.synchronize()
+    n_pk = sum(sizes)
+    losses = view[:, n_pk:n_pk + 12].contiguous().view(torch.float32).reshape(-1, 3).sum(dim=0) if rank == 0 else None
+    gather_kind = "none" if dist is None else (
+        "ONE gather to rank 0 per step (packed detections + the three loss sums in one buffer) by peer-memory pushes + "
+        "device barrier" if peer is not None else "ONE NCCL all_gather_into_tensor per step (packed detections + loss sums)")
     return {"workload": f"batch {STRONG_BATCH} split over {world} GPU(s) = {nb} images per GPU: FCOSHead.detect + FCOSTargetLoss "
-                        f"forward/backward (M<={TRAIN_MAX_GT}) + detection all_gather + loss all_reduce",
+                        f"forward/backward (M<={TRAIN_MAX_GT}) + gather of the detections and the batch-mean losses",
             "scaling": "strong", "images_per_gpu": nb, "ms_per_step": ms_both, "img_per_s": STRONG_BATCH / (ms_both * 1e-3),
             "postprocess_only_ms": ms_post, "postprocess_img_per_s": STRONG_BATCH / (ms_post * 1e-3),
             "train_step_only_ms": ms_train, "how": how, "iters": 20,
             "batch_mean_losses_cls_cnt_reg": [float(v) for v in losses] if losses is not None else None,
-            "collectives": "NCCL all_gather_into_tensor (packed detections) + one all_reduce (3 loss sums)" if world > 1 else "none",
+            "collectives": gather_kind,
             "l2": f"per-GPU inputs {nb * 7.94:.0f} MB per step (> 126 MB L2)"}
 
 
