@@ -1,11 +1,9 @@
 #!/bin/bash
-# A/B timing of library variants: scripts/ab_libs.sh <case list> scratch_libs/libX.so ...   (restores the first at the end)
+# A/B timing of library variants built with build.build(lib=..., defines=[...]):
+#   scripts/ab_libs.sh <case list> scratch_libs/libX.so scratch_libs/libY.so ...
+# (B200DET_LIB makes the package load a variant instead of the in-tree libb200det.so)
 cases=$1; shift
-keep=/tmp/lib_keep.so
-cp pytorch_object_detection_b200/libb200det.so $keep
-for lib in "$@"; do
-  cp "$lib" pytorch_object_detection_b200/libb200det.so
+for lib in pytorch_object_detection_b200/libb200det.so "$@"; do
   echo "== $lib"
-  python scripts/profile_kernels.py --time --only "$cases" 2>&1 | grep median
+  B200DET_LIB=$lib python scripts/profile_kernels.py --time --only "$cases" 2>&1 | grep median
 done
-cp $keep pytorch_object_detection_b200/libb200det.so
