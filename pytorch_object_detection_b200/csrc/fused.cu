@@ -45,8 +45,7 @@ __device__ __forceinline__ bool suppresses(const float4 a, const float aarea, co
   const float w = fmaxf(0.f, __fsub_rn(xx2, xx1));
   const float h = fmaxf(0.f, __fsub_rn(yy2, yy1));
   const float inter = __fmul_rn(w, h);
-  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, carea), inter));
-  return ovr >= thr_up;                                       // == (double)ovr > thr
+  return iou_reaches(inter, __fsub_rn(__fadd_rn(aarea, carea), inter), iou_midpoint(thr_up));   // == (double)ovr > thr
 }
 
 template <bool REG>

@@ -29,6 +29,7 @@ namespace {
 
 constexpr int kPrepThreads = 1024;
 static_assert(kPrepThreads == kHistThreads, "the score histogram is scanned by 1024 threads");
+constexpr int kPrepParts = 8;          // CTAs per image: each gathers a slice of the sorted order
 constexpr int kPrepMaxBin = 64;        // more entries than this in one score bin: the bitonic network sorts instead
 // byte offset of the score histogram behind the keys [n2] and the source map [n] (16-byte aligned)
 __host__ __device__ inline size_t prep_hist_offset(int n, int n2) { return ((size_t)n2 * 8 + (size_t)n * 4 + 15) / 16 * 16; }
@@ -45,41 +46,57 @@ nms_prepare_kernel(const int n, const float* __restrict__ boxes, const float* __
   __shared__ int s_scan[33];
   __shared__ float s_fmax[32];
   const int tid = threadIdx.x;
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   int n2 = next_pow2(n);
   int* srcmap = reinterpret_cast<int*>(sortbuf + n2);
   unsigned* hist = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(sortbuf) + prep_hist_offset(n, n2));
   unsigned long long* tmp = reinterpret_cast<unsigned long long*>(hist + kHistBins);
   const int n_in = in_count ? min(max(in_count[b], 0), n) : n;
   const float* sc = scores + (size_t)b * n;
+  B200DET_STAMP(30);
 
   {
     uint4* h4 = reinterpret_cast<uint4*>(hist);
 #pragma unroll
     for (int q = 0; q < kHistPerThread / 4; ++q) h4[tid + q * kPrepThreads] = make_uint4(0u, 0u, 0u, 0u);
   }
-  // order-preserving threshold compaction: rank = index into the thresholded list (head.py:90-93); the scores are
-  // counted into the histogram on the way (the barriers of the scan order the zero-fill before the first count)
-  int m = 0;
-  for (int base = 0; base < n_in; base += kPrepThreads) {
-    const int i = base + tid;
-    float s = 0.f;
-    const bool ok = (i < n_in) && ((s = sc[i]) >= thr);
-    int total;
-    const int rank = m + block_exclusive_scan(ok ? 1 : 0, s_scan, &total);
-    if (ok) {
-      const uint32_t key = order_key(s);
+  // order-preserving threshold compaction: rank = index into the thresholded list (head.py:90-93).  Warp w owns a
+  // contiguous run of 32-score groups, so the rank is (candidates of the warps before) + (of the warp's groups before)
+  // + (of the lanes before): ballots and ONE block scan, with all the score loads in flight together.  The scores are
+  // counted into the histogram on the way (the barriers of the scan order the zero-fill before the first count).
+  constexpr int kMaxGroups = B200DET_MAX_BOX / kPrepThreads;     // 8 groups of 32 scores per warp
+  const int lane = tid & 31, warp = tid >> 5;
+  const int groups = (n_in + kPrepThreads - 1) / kPrepThreads;
+  const int i0 = warp * groups * 32 + lane;
+  float sv[kMaxGroups];
+#pragma unroll
+  for (int q = 0; q < kMaxGroups; ++q) sv[q] = (q < groups && i0 + q * 32 < n_in) ? sc[i0 + q * 32] : 0.f;
+  unsigned votes[kMaxGroups];
+  int mine = 0;
+#pragma unroll
+  for (int q = 0; q < kMaxGroups; ++q) {
+    votes[q] = __ballot_sync(0xffffffffu, q < groups && i0 + q * 32 < n_in && sv[q] >= thr);
+    mine += __popc(votes[q]);
+  }
+  int m;
+  int run = __shfl_sync(0xffffffffu, block_exclusive_scan(lane == 0 ? mine : 0, s_scan, &m), 0);
+#pragma unroll
+  for (int q = 0; q < kMaxGroups; ++q) {
+    if ((votes[q] >> lane) & 1u) {
+      const int rank = run + __popc(votes[q] & ((1u << lane) - 1u));
+      const uint32_t key = order_key(sv[q]);
       sortbuf[rank] = ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (uint32_t)rank);
-      srcmap[rank] = i;
+      srcmap[rank] = i0 + q * 32;
       atomicAdd(&hist[hist_slot(hist_bin(key))], 1u);
     }
-    m += total;
+    run += __popc(votes[q]);
   }
   if (m == 0) {
-    if (tid == 0) { set.count[b] = 0; set.mode[b] = 0; }
+    if (tid == 0 && blockIdx.x == 0) { set.count[b] = 0; set.mode[b] = 0; }
     return;
   }
   __syncthreads();
+  B200DET_STAMP_NOSYNC(31);
   // Stable descending sort (equal scores: lower rank first).  One-pass radix sort on the score bin: the scan gives every
   // bin's slot range in descending bin order, the keys take a slot of their bin with one atomic, the few keys that share
   // a bin are ranked against each other.  5 000 candidates: ~5 us instead of 88 us for the 8 192-key bitonic network,
@@ -105,11 +122,13 @@ nms_prepare_kernel(const int n, const float* __restrict__ boxes, const float* __
         start += c;
       }
       __syncthreads();
+      B200DET_STAMP_NOSYNC(32);
       for (int i = tid; i < m; i += kPrepThreads) {
         const unsigned long long e = sortbuf[i];
         tmp[atomicAdd(&hist[hist_slot(hist_bin((uint32_t)(e >> 32)))], 1u)] = e;
       }
       __syncthreads();
+      B200DET_STAMP_NOSYNC(33);
       for (int i = tid; i < m; i += kPrepThreads) {
         const unsigned long long e = tmp[i];
         const int bin = hist_bin((uint32_t)(e >> 32));
@@ -120,6 +139,7 @@ nms_prepare_kernel(const int n, const float* __restrict__ boxes, const float* __
         sortbuf[first + rank] = e;
       }
       __syncthreads();
+      B200DET_STAMP_NOSYNC(34);
       sorted = true;
     }
   }
@@ -130,22 +150,61 @@ nms_prepare_kernel(const int n, const float* __restrict__ boxes, const float* __
     bitonic_sort_desc(sortbuf, n2);   // equal scores: lower rank first = stable descending
   }
 
+  // Gather in score order.  Every candidate costs three scattered reads (box, score, class), and one SM's L1 takes a
+  // scattered warp load a line per cycle: 15 000 lines = 7.6 us of the 21 us this kernel took on 5 000 candidates with
+  // one CTA per image.  So an image has kPrepParts CTAs; each sorts its own copy of the keys (like the per-class
+  // kernel: not worth distributing) and gathers one slice of the order.  Four candidates per thread at a time, so
+  // that their loads overlap.  The NMS copy of the boxes (nms_prepare_boxes) is written from the registers: as they
+  // are for a vanilla image; class-offset for a coordinate-trick image, which needs the largest coordinate of the
+  // whole image and has at most 1 000 candidates — CTA 0 gathers those alone, one per thread.
   const size_t o0 = (size_t)b * set.cap;
+  const int mode = (m * 4 <= kTrickMaxNumel) ? kModeTrick : kModeVanilla;
+  if (mode == kModeTrick && blockIdx.x != 0) return;
+  const int slice = mode == kModeTrick ? m : (m + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int lo = mode == kModeTrick ? 0 : (int)blockIdx.x * slice, hi = min(m, lo + slice);
   float vmax = -CUDART_INF_F;
-  for (int i = tid; i < m; i += kPrepThreads) {
-    const unsigned long long e = sortbuf[i];
-    const int rank = (int)(0xffffffffu - (uint32_t)(e & 0xffffffffull));
-    const int src = srcmap[rank];
-    const float4 bx = reinterpret_cast<const float4*>(boxes)[(size_t)b * n + src];
-    set.score[o0 + i] = sc[src];
-    set.cls[o0 + i] = (int)classes[(size_t)b * n + src];
-    set.src[o0 + i] = rank;
-    reinterpret_cast<float4*>(set.box)[o0 + i] = bx;
-    vmax = fmaxf(vmax, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+  constexpr int kGather = 4;
+  float4 bx[kGather];
+  int cl[kGather];
+  for (int base = lo; base < hi; base += kPrepThreads * kGather) {
+    float s[kGather];
+    int rank[kGather];
+#pragma unroll
+    for (int u = 0; u < kGather; ++u) {
+      const int i = base + u * kPrepThreads + tid;
+      if (i < hi) {
+        rank[u] = (int)(0xffffffffu - (uint32_t)(sortbuf[i] & 0xffffffffull));
+        const int src = srcmap[rank[u]];
+        bx[u] = reinterpret_cast<const float4*>(boxes)[(size_t)b * n + src];
+        s[u] = sc[src];
+        cl[u] = (int)classes[(size_t)b * n + src];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGather; ++u) {
+      const int i = base + u * kPrepThreads + tid;
+      if (i < hi) {
+        set.score[o0 + i] = s[u];
+        set.cls[o0 + i] = cl[u];
+        set.src[o0 + i] = rank[u];
+        reinterpret_cast<float4*>(set.box)[o0 + i] = bx[u];
+        if (mode == kModeVanilla) reinterpret_cast<float4*>(set.nms_box)[o0 + i] = bx[u];
+        vmax = fmaxf(vmax, fmaxf(fmaxf(bx[u].x, bx[u].y), fmaxf(bx[u].z, bx[u].w)));
+      }
+    }
   }
-  vmax = block_max(vmax, s_fmax);
-  nms_prepare_boxes(set, b, m, vmax, tid, kPrepThreads);
-  if (tid == 0) set.count[b] = m;
+  B200DET_STAMP_NOSYNC(35);
+  if (mode == kModeTrick) {                                      // m <= 1000: the thread's one box is bx[0]
+    static_assert(kTrickMaxNumel / 4 <= kPrepThreads, "a coordinate-trick image has at most one candidate per thread");
+    vmax = block_max(vmax, s_fmax);
+    if (tid < m) {
+      const float off = __fmul_rn((float)cl[0], __fadd_rn(vmax, 1.0f));
+      reinterpret_cast<float4*>(set.nms_box)[o0 + tid] =
+          make_float4(__fadd_rn(bx[0].x, off), __fadd_rn(bx[0].y, off), __fadd_rn(bx[0].z, off), __fadd_rn(bx[0].w, off));
+    }
+  }
+  if (tid == 0 && blockIdx.x == 0) { set.mode[b] = mode; set.count[b] = m; }
+  B200DET_STAMP(36);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -272,7 +331,7 @@ nms_scan_smem_kernel(const CandSet set, const int wblocks, const int cap_pad,
         keep = ~cur & valid;                                 // empty diagonal tile
       } else {
         const unsigned long long* diag = sm + col_off(rb) + rb * kNmsTile;
-        keep = resolve_block(cur, valid, diag[lane], diag[lane + 32], lane);
+        keep = resolve_block<64>(cur, valid, diag[lane], diag[lane + 32], lane);
       }
       if (lane == 0) keepw[rb] = keep;
       const bool k0 = (keep >> lane) & 1ull, k1 = (keep >> (lane + 32)) & 1ull;
@@ -376,7 +435,7 @@ nms_scan_ring_kernel(const CandSet set, const int wblocks, const int cap_pad,
     const int rows = min(kNmsTile, n - rb * kNmsTile);
     const unsigned long long valid = rows == kNmsTile ? ~0ull : ((1ull << rows) - 1ull);
     if (warp == 0) {
-      const unsigned long long keep = resolve_block(removed[rb], valid, chunk[lane], chunk[lane + 32], lane);
+      const unsigned long long keep = resolve_block<64>(removed[rb], valid, chunk[lane], chunk[lane + 32], lane);
       if (lane == 0) s_keep = keep;
     }
     __syncthreads();
@@ -529,7 +588,7 @@ extern "C" int b200det_batched_nms(int batch, int n, const float* boxes, const f
   const size_t smem = prep_hist_offset(n, n2) + (size_t)kHistBins * 4 + (size_t)n * 8;
   int rc = set_smem(nms_prepare_kernel, smem);
   if (rc) return rc;
-  nms_prepare_kernel<<<batch, kPrepThreads, smem, st>>>(n, boxes, scores, reinterpret_cast<const long long*>(classes),
+  nms_prepare_kernel<<<dim3(kPrepParts, batch), kPrepThreads, smem, st>>>(n, boxes, scores, reinterpret_cast<const long long*>(classes),
                                                        in_count, score_thr, set);
   rc = check_launch();
   if (rc) return rc;

@@ -4,6 +4,22 @@
 
 namespace b200det {
 
+// The reference's test `fl(inter / uni) >= thr_up` without the division (an IEEE fp32 divide is ~18 instructions
+// with a slow path; this is two conversions, one DMUL and one DSETP).  Rounding is monotone, so the rounded quotient
+// reaches thr_up exactly when the real quotient lies above the midpoint `mid` of thr_up and the float below it
+// (25 significant bits, exact as a double), i.e. when inter > mid * uni — both sides exact in double arithmetic
+// (24 + 25 <= 53 bits).  The tie inter == mid * uni cannot happen for a normal thr_up: mid is an odd 25-bit number, so
+// the product has at least 25 significant bits and is no float; 0 / 0, infinities and NaN compare false on both sides.
+// (Thresholds >= 0 only: ZERO_SUP keeps the division.  thr_up = the smallest float above the double threshold,
+// nms_threshold_params.)
+__device__ __forceinline__ double iou_midpoint(const float thr_up) {
+  const float below = __int_as_float(__float_as_int(thr_up) - 1);      // thr_up > 0
+  return 0.5 * ((double)below + (double)thr_up);
+}
+__device__ __forceinline__ bool iou_reaches(const float inter, const float uni, const double mid) {
+  return (double)inter > mid * (double)uni;
+}
+
 // One row of a 64x64 mask tile: box `a` against the 64 column boxes staged in shared memory
 // (cbox / carea / ccls, 64 entries).  Pass 1 is branch-free and fully unrolled (one broadcast
 // LDS.128, 4 min/max, 2 compares per pair): w > 0 <=> min(x2) > max(x1) exactly in IEEE
@@ -28,14 +44,15 @@ __device__ __forceinline__ unsigned long long mask_row_bits(const float4 a, cons
   }
   unsigned long long bits = ((unsigned long long)hi << 32) | lo;
   // pass 2 (rare): the reference's exact IoU expression for the candidates only
+  const double mid = ZERO_SUP ? 0.0 : iou_midpoint(thr_up);
   for (unsigned long long m = bits; m; m &= m - 1ull) {
     const int j = __ffsll((long long)m) - 1;
     const float4 c = cbox[j];
     const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, c.z), fmaxf(a.x, c.x)));
     const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, c.w), fmaxf(a.y, c.y)));
     const float inter = __fmul_rn(w, h);
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, carea[j]), inter));
-    bool sup = ovr >= thr_up;                        // == (double)ovr > thr, see launch_nms
+    const float uni = __fsub_rn(__fadd_rn(aarea, carea[j]), inter);
+    bool sup = ZERO_SUP ? __fdiv_rn(inter, uni) >= thr_up : iou_reaches(inter, uni, mid);   // == (double)ovr > thr, see launch_nms
     if (same_class_only) sup = sup && (ccls[j] == acls);
     if (!sup) bits &= ~(1ull << j);
   }
@@ -57,16 +74,86 @@ __device__ __forceinline__ unsigned mask_row_bits_part(const float4 a, const flo
     const bool overlap = ZERO_SUP || (fminf(a.z, c.z) > fmaxf(a.x, c.x) && fminf(a.w, c.w) > fmaxf(a.y, c.y));
     bits |= overlap ? (1u << j) : 0u;
   }
-  for (unsigned m = bits; m; m &= m - 1u) {
-    const int j = __ffs((int)m) - 1;
+  const double mid = ZERO_SUP ? 0.0 : iou_midpoint(thr_up);
+  auto reaches = [&](const int j) {
     const float4 c = cbox[j];
     const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, c.z), fmaxf(a.x, c.x)));
     const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, c.w), fmaxf(a.y, c.y)));
     const float inter = __fmul_rn(w, h);
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, carea[j]), inter));
-    if (!(ovr >= thr_up)) bits &= ~(1u << j);            // == !((double)ovr > thr), see launch_nms
+    const float uni = __fsub_rn(__fadd_rn(aarea, carea[j]), inter);
+    return ZERO_SUP ? __fdiv_rn(inter, uni) >= thr_up : iou_reaches(inter, uni, mid);   // == (double)ovr > thr, see launch_nms
+  };
+  // A crowd (most pairs of a class overlap): every column, branch-free and unrolled — the candidate loop below would
+  // run its serial chain (find bit, load, test) as many times as the busiest lane has candidates.
+  // (Called by whole warps: the vote is over all 32 lanes.)
+  if (__any_sync(0xffffffffu, __popc(bits) > NC / 4)) {
+    unsigned sup = 0u;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) sup |= reaches(j) ? (1u << j) : 0u;
+    return bits & sup;
+  }
+  for (unsigned m = bits; m; m &= m - 1u) {
+    const int j = __ffs((int)m) - 1;
+    if (!reaches(j)) bits &= ~(1u << j);
   }
   return bits;
+}
+
+// Two rows (a0, a1) against the first NC staged columns in ONE branch-free pass, for crowds where most pairs of a
+// class overlap (the per-class kernel's work unit).  The division is bracketed instead of evaluated: with uni > 0,
+//   inter >  fl(thr_up * uni)  =>  inter >= thr_up * uni  =>  fl(inter / uni) >= thr_up        (suppressed)
+//   inter <  fl(below * uni)   =>  inter <= below * uni   =>  fl(inter / uni) <= below < thr_up (not suppressed)
+// (a float above / below a rounded product is not below / above the real product; `below` = the float under thr_up),
+// which leaves a band one or two ulps wide — about one pair in 10^7 — to the exact test iou_reaches().
+// 19 instructions per pair (the column loads are shared by the two rows) against ~30 for candidate pass + exact pass.
+// Rows that overlap nothing (kNoBox) yield no bits; !TWO_ROWS skips a1.  Thresholds >= 0 only.
+template <int NC, bool TWO_ROWS>
+__device__ __forceinline__ void mask_rows2_part(const float4 a0, const float4 a1, const float4* cbox, const float* carea,
+                                                const float thr_up, unsigned& bits0, unsigned& bits1) {
+  const unsigned cbase = (unsigned)__cvta_generic_to_shared(cbox);
+  const float below = __int_as_float(__float_as_int(thr_up) - 1);
+  const float area0 = __fmul_rn(__fsub_rn(a0.z, a0.x), __fsub_rn(a0.w, a0.y));
+  const float area1 = __fmul_rn(__fsub_rn(a1.z, a1.x), __fsub_rn(a1.w, a1.y));
+  unsigned s0 = 0u, s1 = 0u, m0 = 0u, m1 = 0u;                 // sure / maybe bits of the two rows
+  auto pair = [&](const float4 a, const float aarea, const float4 c, const float ca, const unsigned bit, unsigned& sure,
+                  unsigned& maybe) {
+    const float xx1 = fmaxf(a.x, c.x), yy1 = fmaxf(a.y, c.y), xx2 = fminf(a.z, c.z), yy2 = fminf(a.w, c.w);
+    const bool overlap = xx2 > xx1 && yy2 > yy1;               // both boxes proper, uni > 0
+    const float inter = __fmul_rn(__fsub_rn(xx2, xx1), __fsub_rn(yy2, yy1));   // (= the reference's clamped w * h here)
+    const float uni = __fsub_rn(__fadd_rn(aarea, ca), inter);
+    const bool yes = overlap && inter > __fmul_rn(thr_up, uni);
+    const bool open = overlap && inter >= __fmul_rn(below, uni);
+    sure |= yes ? bit : 0u;
+    maybe |= open ? bit : 0u;
+  };
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    float4 c;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "r"(cbase + j * 16));
+    const float ca = carea[j];
+    pair(a0, area0, c, ca, 1u << j, s0, m0);
+    if (TWO_ROWS) pair(a1, area1, c, ca, 1u << j, s1, m1);
+  }
+  m0 &= ~s0;
+  m1 &= ~s1;
+  if (__any_sync(0xffffffffu, (m0 | m1) != 0u)) {              // the undecided band: the exact test
+    const double mid = iou_midpoint(thr_up);
+    auto settle = [&](const float4 a, const float aarea, unsigned m, unsigned& sure) {
+      for (; m; m &= m - 1u) {
+        const int j = __ffs((int)m) - 1;
+        const float4 c = cbox[j];
+        const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, c.z), fmaxf(a.x, c.x)));
+        const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, c.w), fmaxf(a.y, c.y)));
+        const float inter = __fmul_rn(w, h);
+        if (iou_reaches(inter, __fsub_rn(__fadd_rn(aarea, carea[j]), inter), mid)) sure |= 1u << j;
+      }
+    };
+    settle(a0, area0, m0, s0);
+    settle(a1, area1, m1, s1);
+  }
+  bits0 = s0;
+  bits1 = s1;
 }
 
 // column-block-major packed upper triangle: column block w holds the words of rows [0, (w+1)*64)
@@ -89,6 +176,9 @@ __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int s
 // held lane-per-row (d0: row lane, d1: row lane+32).  If no still-alive row suppresses another
 // still-alive row (one warp OR-reduction) all alive rows are kept at once; otherwise the 64 rows
 // are walked serially out of registers (shuffles), the greedy rule of torchvision's nms kernel.
+// UNROLL = 64 turns the bit tests of the walk into constants (measured on the dense path: 1 000 crowded candidates
+// x 16 images 60.9 -> 54.8 us); the fused kernel, where the walk is rare, keeps the compact loop.
+template <int UNROLL = 8>
 __device__ __forceinline__ unsigned long long resolve_block(const unsigned long long cur, const unsigned long long valid,
                                                             const unsigned long long d0, const unsigned long long d1,
                                                             const int lane) {
@@ -99,7 +189,7 @@ __device__ __forceinline__ unsigned long long resolve_block(const unsigned long 
   // shuffle depends on the previous step, ~40 cycles each, while here the 64 row fetches are independent of the
   // chain and pipeline; 1 000 crowded candidates x 16 images: 80.6 vs 68.6 us.)
   unsigned long long c = cur, keep = 0ull;
-#pragma unroll 8
+#pragma unroll(UNROLL)
   for (int i = 0; i < kNmsTile; ++i) {
     const unsigned long long di = shfl64(i < 32 ? d0 : d1, i & 31);
     const bool alive = ((valid >> i) & 1ull) && !((c >> i) & 1ull);

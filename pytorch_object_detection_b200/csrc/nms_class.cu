@@ -31,6 +31,9 @@ constexpr int kClassThreads = 1024;
 constexpr int kClassWarps = kClassThreads / 32;
 constexpr int kClassMaxSeg = 1024;            // boxes of one class handled by a warp (16 blocks of 64)
 constexpr int kRankBits = 13;                 // rank < 8192 = B200DET_MAX_BOX
+constexpr int kOrderMax = 256;                // classes dealt to the CTAs in order of size up to this many
+constexpr int kDenseClasses = 256;            // class ids below this take the table-driven stable split
+constexpr int kTileBudget = (kClassMaxSeg / 64) * (kClassMaxSeg / 64 + 1) / 2;   // 136 tiles of 64 x 64 bits in shared memory
 
 // ascending bitonic sort of n (power of two) 32-bit keys in shared memory
 __device__ __forceinline__ void bitonic_sort_asc_u32(unsigned* buf, const int n) {
@@ -55,7 +58,9 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
   __shared__ int s_scan[33];
   __shared__ float s_fmax[32];
   __shared__ int s_pre[B200DET_MAX_BOX / 64 + 1];
-  __shared__ unsigned short s_big[B200DET_MAX_BOX / 64 + 1];     // segments longer than 64 boxes: fewer than n / 64
+  __shared__ unsigned short s_cstart[kDenseClasses];             // first slot of a class (dense-id path)
+  __shared__ unsigned short s_toff[kTileBudget + 1];            // first tile of the batch's classes
+  __shared__ unsigned short s_ord[kOrderMax];                   // classes by size, largest first
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -80,104 +85,162 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
   const size_t q0 = (size_t)b * out.stride;
 
   // ---- 1. (class, rank) keys, sorted: one contiguous score-ordered segment per class -----------------------
-  // Counting sort on the class (ids below kHistBins; the histogram and the scratch copy of the keys live where the
-  // column staging and the tile bits will be): the scan gives every class its slot range, the keys take a slot of
-  // their class with one atomic and are then ranked inside the class by their score rank.  5 000 candidates: ~5 us
-  // instead of 45 us for the 8 192-key bitonic network, which stays for class ids it cannot bin.
+  // The candidate list arrives in score order, so this is a STABLE split by class.
+  // (a) Class ids below kDenseClasses (COCO, VOC): warp w takes a contiguous run of 32-key groups; in a group the
+  //     lanes of one class find each other with match.any, and a per-warp count table [warp][class] gives every key
+  //     its position among the warp's keys of its class.  One pass down the table's columns turns the counts into
+  //     offsets, one scan over the classes gives the class starts (= the segments) — ~2 us for 5 000 candidates, and
+  //     nothing is ranked or compared.
+  // (b) Otherwise a counting sort on the class (ids below kHistBins; the histogram and the scratch copy of the keys
+  //     live where the column staging and the tile bits will be) with the keys ranked inside their class afterwards,
+  //     and the 8 192-key bitonic network for class ids it cannot bin.
   static_assert(kClassThreads == kHistThreads, "the class histogram is scanned by 1024 threads");
   unsigned* chist = reinterpret_cast<unsigned*>(tmask);                 // [kHistBins] (tmask holds 136 x 64 x 8 bytes)
   unsigned* tmpk = reinterpret_cast<unsigned*>(cbox_all);               // [n] (cbox_all holds 32 x 64 x 16 bytes)
+  unsigned short* wcnt = reinterpret_cast<unsigned short*>(tmask);      // [kClassWarps][kDenseClasses]
   static_assert((size_t)(kClassMaxSeg / kNmsTile) * (kClassMaxSeg / kNmsTile + 1) / 2 * kNmsTile * 8 >= (size_t)kHistBins * 4,
                 "class histogram aliases the tile bits");
   static_assert((size_t)kClassWarps * kNmsTile * sizeof(float4) >= (size_t)B200DET_MAX_BOX * 4, "key scratch aliases the column staging");
-  {
-    uint4* h4 = reinterpret_cast<uint4*>(chist);
-#pragma unroll
-    for (int q = 0; q < kHistPerThread / 4; ++q) h4[tid + q * kClassThreads] = make_uint4(0u, 0u, 0u, 0u);
-  }
-  __syncthreads();
-  float cmax = 0.f, cbig = 0.f;
-  for (int i = tid; i < n2; i += kClassThreads) {
-    unsigned key = 0xffffffffu;
-    if (i < n) {
-      const int c = set.cls[o0 + i];
-      cmax = fmaxf(cmax, (c < 0 || c >= (1 << (32 - kRankBits - 1))) ? 1.f : 0.f);
-      cbig = fmaxf(cbig, (c < 0 || c >= kHistBins) ? 1.f : 0.f);
-      key = ((unsigned)c << kRankBits) | (unsigned)i;
-      if (c >= 0 && c < kHistBins) atomicAdd(&chist[hist_slot(c)], 1u);
-    }
-    keys[i] = key;
-  }
+  static_assert(kClassWarps * kDenseClasses * 2 == kClassThreads * 16, "one uint4 per thread clears the count table");
+  reinterpret_cast<uint4*>(wcnt)[tid] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < kwords; i += kClassThreads) keepbits[i] = 0u;
-  const bool bad_class = block_max(cmax, s_fmax) > 0.f;          // also the barrier before the sort
-  const bool unbinned = block_max(cbig, s_fmax) > 0.f;
-  B200DET_STAMP(1);
-  if (!unbinned) {
-    unsigned hb[kHistPerThread];                                  // thread t: classes [16 t, 16 t + 16), ascending
-    int mine = 0;
+  __syncthreads();
+  constexpr int kGroupsPerWarp = B200DET_MAX_BOX / 32 / kClassWarps;   // 8
+  const int gpw = ((n + 31) / 32 + kClassWarps - 1) / kClassWarps;     // groups per warp in this image
+  int cls_q[kGroupsPerWarp];
+  unsigned short loc_q[kGroupsPerWarp];
+  bool cmax = false, sparse = false;
 #pragma unroll
-    for (int q = 0; q < kHistPerThread; ++q) {
-      hb[q] = chist[q * kClassThreads + tid];
-      mine += (int)hb[q];
-    }
-    int total;
-    unsigned start = (unsigned)block_exclusive_scan(mine, s_scan, &total);
-#pragma unroll
-    for (int q = 0; q < kHistPerThread; ++q) {                   // counts -> first slot of the class
-      const unsigned c = hb[q];
-      chist[q * kClassThreads + tid] = start;
-      start += c;
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += kClassThreads) {
-      const unsigned key = keys[i];
-      tmpk[atomicAdd(&chist[hist_slot((int)(key >> kRankBits))], 1u)] = key;
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += kClassThreads) {
-      const unsigned key = tmpk[i];
-      const int c = (int)(key >> kRankBits);
-      const unsigned first = c == 0 ? 0u : chist[hist_slot(c - 1)];     // = end of the classes below
-      const unsigned end = chist[hist_slot(c)];
-      unsigned rank = 0;
-      for (unsigned j = first; j < end; ++j) rank += tmpk[j] < key ? 1u : 0u;
-      keys[first + rank] = key;
-    }
-    __syncthreads();
-  } else {
-    bitonic_sort_asc_u32(keys, n2);
+  for (int q = 0; q < kGroupsPerWarp; ++q) {
+    const int i = (warp * gpw + q) * 32 + lane;
+    cls_q[q] = (q < gpw && i < n) ? set.cls[o0 + i] : 0;
   }
-  B200DET_STAMP(2);
-  // segment starts (order-preserving compaction) and the longest segment
+  unsigned short* wrow = wcnt + warp * kDenseClasses;
+#pragma unroll
+  for (int q = 0; q < kGroupsPerWarp; ++q) {
+    if (q >= gpw) { cls_q[q] = -1; continue; }                   // (uniform over the CTA)
+    const int i = (warp * gpw + q) * 32 + lane;
+    const int c = cls_q[q];
+    const bool in = i < n;
+    const bool ok = in && c >= 0 && c < kDenseClasses;
+    sparse = sparse || (in && !ok);
+    cmax = cmax || (in && (c < 0 || c >= (1 << (32 - kRankBits - 1))));
+    const unsigned peers = __match_any_sync(0xffffffffu, ok ? c : kDenseClasses + lane);
+    const int r = __popc(peers & ((1u << lane) - 1u));
+    const unsigned short base = ok ? wrow[c] : (unsigned short)0;
+    __syncwarp();
+    if (ok && r == 0) wrow[c] = (unsigned short)(base + __popc(peers));
+    __syncwarp();
+    cls_q[q] = ok ? c : -1;
+    loc_q[q] = (unsigned short)(base + r);
+  }
+  const bool bad_class = __syncthreads_or(cmax) != 0;            // also the barrier after the counts
+  const bool dense = __syncthreads_or(sparse) == 0;
+  B200DET_STAMP(1);
   int n_seg = 0;
   float longest = 0.f;
-  for (int base = 0; base < n; base += kClassThreads) {
-    const int i = base + tid;
-    const bool start = i < n && (i == 0 || (keys[i] >> kRankBits) != (keys[i - 1] >> kRankBits));
-    int total;
-    const int pos = n_seg + block_exclusive_scan(start ? 1 : 0, s_scan, &total);
-    if (start) seg[pos] = (unsigned short)i;
-    n_seg += total;
+  if (dense) {
+    int tot = 0;
+    if (tid < kDenseClasses) {
+#pragma unroll 8
+      for (int w = 0; w < kClassWarps; ++w) {                      // counts -> offset of the warp inside the class
+        const int v = wcnt[w * kDenseClasses + tid];
+        wcnt[w * kDenseClasses + tid] = (unsigned short)tot;
+        tot += v;
+      }
+    }
+    int total;                                                   // low half: keys, high half: classes present
+    const int ex = block_exclusive_scan(tot | (tot > 0 ? 1 << 16 : 0), s_scan, &total);
+    if (tid < kDenseClasses) {
+      s_cstart[tid] = (unsigned short)(ex & 0xffff);
+      if (tot > 0) seg[ex >> 16] = (unsigned short)(ex & 0xffff);
+    }
+    n_seg = total >> 16;
+    longest = block_max((float)tot, s_fmax);                     // also the barrier before the placement
+#pragma unroll
+    for (int q = 0; q < kGroupsPerWarp; ++q) {
+      const int c = cls_q[q];
+      if (c < 0) continue;
+      const unsigned i = (unsigned)((warp * gpw + q) * 32 + lane);
+      keys[(int)s_cstart[c] + (int)wrow[c] + (int)loc_q[q]] = ((unsigned)c << kRankBits) | i;
+    }
+    __syncthreads();
+    B200DET_STAMP(2);
+  } else {
+    {
+      uint4* h4 = reinterpret_cast<uint4*>(chist);
+#pragma unroll
+      for (int q = 0; q < kHistPerThread / 4; ++q) h4[tid + q * kClassThreads] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    float cbig = 0.f;
+    for (int i = tid; i < n2; i += kClassThreads) {
+      unsigned key = 0xffffffffu;
+      if (i < n) {
+        const int c = set.cls[o0 + i];
+        cbig = fmaxf(cbig, (c < 0 || c >= kHistBins) ? 1.f : 0.f);
+        key = ((unsigned)c << kRankBits) | (unsigned)i;
+        if (c >= 0 && c < kHistBins) atomicAdd(&chist[hist_slot(c)], 1u);
+      }
+      keys[i] = key;
+    }
+    const bool unbinned = block_max(cbig, s_fmax) > 0.f;         // also the barrier before the sort
+    if (!unbinned) {
+      unsigned hb[kHistPerThread];                                // thread t: classes [16 t, 16 t + 16), ascending
+      int mine = 0;
+#pragma unroll
+      for (int q = 0; q < kHistPerThread; ++q) {
+        hb[q] = chist[q * kClassThreads + tid];
+        mine += (int)hb[q];
+      }
+      int total;
+      unsigned start = (unsigned)block_exclusive_scan(mine, s_scan, &total);
+#pragma unroll
+      for (int q = 0; q < kHistPerThread; ++q) {                 // counts -> first slot of the class
+        const unsigned c = hb[q];
+        chist[q * kClassThreads + tid] = start;
+        start += c;
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += kClassThreads) {
+        const unsigned key = keys[i];
+        tmpk[atomicAdd(&chist[hist_slot((int)(key >> kRankBits))], 1u)] = key;
+      }
+      __syncthreads();
+      for (int i = tid; i < n; i += kClassThreads) {
+        const unsigned key = tmpk[i];
+        const int c = (int)(key >> kRankBits);
+        const unsigned first = c == 0 ? 0u : chist[hist_slot(c - 1)];   // = end of the classes below
+        const unsigned end = chist[hist_slot(c)];
+        unsigned rank = 0;
+        for (unsigned j = first; j < end; ++j) rank += tmpk[j] < key ? 1u : 0u;
+        keys[first + rank] = key;
+      }
+      __syncthreads();
+    } else {
+      bitonic_sort_asc_u32(keys, n2);
+    }
+    B200DET_STAMP(2);
+    // segment starts (order-preserving compaction) and the longest segment
+    for (int base = 0; base < n; base += kClassThreads) {
+      const int i = base + tid;
+      const bool start = i < n && (i == 0 || (keys[i] >> kRankBits) != (keys[i - 1] >> kRankBits));
+      int total;
+      const int pos = n_seg + block_exclusive_scan(start ? 1 : 0, s_scan, &total);
+      if (start) seg[pos] = (unsigned short)i;
+      n_seg += total;
+    }
+    __syncthreads();
+    for (int s = tid; s < n_seg; s += kClassThreads)
+      longest = fmaxf(longest, (float)((s + 1 < n_seg ? (int)seg[s + 1] : n) - (int)seg[s]));
+    longest = block_max(longest, s_fmax);
   }
-  __syncthreads();
-  for (int s = tid; s < n_seg; s += kClassThreads)
-    longest = fmaxf(longest, (float)((s + 1 < n_seg ? (int)seg[s + 1] : n) - (int)seg[s]));
-  longest = block_max(longest, s_fmax);
   if (bad_class || longest > (float)kClassMaxSeg) return;        // left to the dense path (mode stays vanilla)
-  int n_big = 0;                                                 // classes of more than one 64-box block
-  for (int base = 0; base < n_seg; base += kClassThreads) {
-    const int sg = base + tid;
-    const bool big = sg < n_seg && ((sg + 1 < n_seg ? (int)seg[sg + 1] : n) - (int)seg[sg]) > kNmsTile;
-    int total;
-    const int pos = n_big + block_exclusive_scan(big ? 1 : 0, s_scan, &total);
-    if (big) s_big[pos] = (unsigned short)sg;
-    n_big += total;
-  }
   cluster.sync();                                                // CTA 0's keep bitmap is clear; every CTA runs
   unsigned* image_keep = cluster.map_shared_rank(keepbits, 0);   // kept ranks meet in CTA 0 (32-bit atomicOr, DSMEM)
 
   B200DET_STAMP(3);
-  // ---- 2. one warp per class segment ---------------------------------------------------------------------------
+  // ---- 2. every class on its own ---------------------------------------------------------------------------------
   float4* cbox = cbox_all + warp * kNmsTile;
   float* carea = carea_all + warp * kNmsTile;
   const float4 kNoBox = make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);   // overlaps nothing
@@ -185,100 +248,134 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
   auto load_box = [&](const int pos, const int end) {
     return pos < end ? reinterpret_cast<const float4*>(set.box)[o0 + (keys[pos] & ((1u << kRankBits) - 1u))] : kNoBox;
   };
-  auto stage_cols = [&](const float4 c0, const float4 c1, const bool ok0, const bool ok1) {
-    __syncwarp();
-    cbox[lane] = c0;
-    cbox[lane + 32] = c1;
-    carea[lane] = ok0 ? __fmul_rn(__fsub_rn(c0.z, c0.x), __fsub_rn(c0.w, c0.y)) : kNoArea;
-    carea[lane + 32] = ok1 ? __fmul_rn(__fsub_rn(c1.z, c1.x), __fsub_rn(c1.w, c1.y)) : kNoArea;
-    __syncwarp();
-  };
   auto rank_of = [&](const int pos) { return keys[pos] & ((1u << kRankBits) - 1u); };
   auto keep_rank = [&](const unsigned r) { atomicOr(image_keep + (r >> 5), 1u << (r & 31)); };
 
-  // 2a. classes of more than 64 boxes, one at a time per CTA (dealt over the cluster): all warps evaluate the
-  //     class's tiles into shared memory, then one warp runs the greedy pass over the stored bits.
-  for (int k = rank; k < n_big; k += kClassCluster) {
-    const int sg = s_big[k];
-    const int s0 = seg[sg], s1 = sg + 1 < n_seg ? (int)seg[sg + 1] : n;
-    const int W = (s1 - s0 + kNmsTile - 1) / kNmsTile;           // 2 .. 16 blocks
-    const int tiles = W * (W + 1) / 2;
-    // work unit = (tile, 16-column part): a class of 100-400 boxes has 3-28 tiles, too few for 32 warps
-    constexpr int kPart = 16, kParts = kNmsTile / kPart;
+  // The classes are dealt round-robin to the cluster's CTAs.  A CTA takes its classes in batches whose tiles
+  // (64 x 64 blocks of the upper triangle, one for a class of <= 64 boxes) fit the tile buffer — for 5 000 candidates
+  // of 80 classes all ten classes of a CTA are one batch — and per batch
+  //   * ALL warps evaluate the batch's tiles into shared memory, a (tile, 16-column part) unit at a time: a single
+  //     warp needs ~10 us of dependent issue for a whole tile, so the pair tests are spread as thin as they go;
+  //   * then one warp per class runs the greedy pass over the stored bits (a serial chain), the classes in parallel.
+  constexpr int kPart = 16, kParts = kNmsTile / kPart;
+  // Dealing: the classes in order of size, largest first, laid out boustrophedon over the CTAs (0..7, 7..0, ...), so
+  // every CTA gets a like share of the pair tests (plain round-robin left the slowest CTA of a cluster ~13 us behind
+  // the first on 5 000 candidates of 80 classes).  The order costs one n_seg-long count per class, so it is taken up
+  // to kOrderMax classes; beyond, round-robin.
+  const bool ordered = n_seg <= kOrderMax;
+  if (ordered && tid < n_seg) {
+    const int mine = (tid + 1 < n_seg ? (int)seg[tid + 1] : n) - (int)seg[tid];
+    int before = 0;                                              // classes ahead of this one: larger, or equal and earlier
+    for (int o = 0; o < n_seg; ++o) {
+      const int other = (o + 1 < n_seg ? (int)seg[o + 1] : n) - (int)seg[o];
+      before += (other > mine || (other == mine && o < tid)) ? 1 : 0;
+    }
+    s_ord[before] = (unsigned short)tid;
+  }
+  __syncthreads();
+  struct ClassSeg { int s0, s1, W; };
+  auto my_class = [&](const int j) {                            // the j-th class of this CTA
+    const int sg = ordered ? (int)s_ord[j * kClassCluster + ((j & 1) ? kClassCluster - 1 - rank : rank)]
+                           : rank + j * kClassCluster;
+    ClassSeg c;
+    c.s0 = seg[sg];
+    c.s1 = sg + 1 < n_seg ? (int)seg[sg + 1] : n;
+    c.W = (c.s1 - c.s0 + kNmsTile - 1) / kNmsTile;              // 1 .. 16 blocks
+    return c;
+  };
+  int my_n;
+  {
+    const int rows = n_seg / kClassCluster, left = n_seg - rows * kClassCluster;
+    const int col = (ordered && (rows & 1)) ? kClassCluster - 1 - rank : rank;
+    my_n = rows + (col < left ? 1 : 0);
+  }
+  for (int j0 = 0; j0 < my_n;) {
+    int cnt = 0, tiles = 0;                                      // the batch: classes j0 .. j0 + cnt - 1
+    while (j0 + cnt < my_n && cnt < kTileBudget) {
+      const int W = my_class(j0 + cnt).W;
+      const int t = W * (W + 1) / 2;
+      if (tiles + t > kTileBudget) break;                        // (a class alone always fits: W <= 16)
+      if (tid == 0) s_toff[cnt] = (unsigned short)tiles;
+      tiles += t;
+      ++cnt;
+    }
+    if (tid == 0) s_toff[cnt] = (unsigned short)tiles;
     for (int i = tid; i < tiles * kNmsTile; i += kClassThreads) tmask[i] = 0ull;
     __syncthreads();
     for (int unit = warp; unit < tiles * kParts; unit += kClassWarps) {
-      const int tile = unit / kParts, part = unit - tile * kParts;
-      int rb = 0, rem = tile;
-      while (rem >= W - rb) { rem -= W - rb; ++rb; }             // row-major upper triangle
+      const int tile_g = unit / kParts, part = unit - tile_g * kParts;
+      int lo = 0, hi = cnt;                                      // s_toff[lo] <= tile_g < s_toff[hi]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)s_toff[mid] <= tile_g) lo = mid; else hi = mid;
+      }
+      const ClassSeg c = my_class(j0 + lo);
+      int rb = 0, rem = tile_g - (int)s_toff[lo];
+      while (rem >= c.W - rb) { rem -= c.W - rb; ++rb; }          // row-major upper triangle
       const int cb = rb + rem;
-      const int r0 = s0 + rb * kNmsTile + lane, r1 = r0 + 32;
-      const int c0 = s0 + cb * kNmsTile + part * kPart + lane;   // (lanes 0-15 stage the part's columns)
-      const float4 a0 = load_box(r0, s1), a1 = load_box(r1, s1);
-      const float4 cc = lane < kPart ? load_box(c0, s1) : kNoBox;
+      const int col0 = c.s0 + cb * kNmsTile + part * kPart;
+      if (col0 >= c.s1) continue;                                // no column in this part
+      const bool diag = cb == rb;
+      const int r0 = c.s0 + rb * kNmsTile + lane, r1 = r0 + 32;
+      const bool need1 = !(diag && part < 2);                    // diagonal tile: rows 32-63 only see columns > 32
+      const float4 a0 = load_box(r0, c.s1), a1 = need1 ? load_box(r1, c.s1) : kNoBox;
+      const float4 cc = lane < kPart ? load_box(col0 + lane, c.s1) : kNoBox;   // (lanes 0-15 stage the columns)
       __syncwarp();
       if (lane < kPart) {
         cbox[lane] = cc;
-        carea[lane] = c0 < s1 ? __fmul_rn(__fsub_rn(cc.z, cc.x), __fsub_rn(cc.w, cc.y)) : kNoArea;
+        carea[lane] = col0 + lane < c.s1 ? __fmul_rn(__fsub_rn(cc.z, cc.x), __fsub_rn(cc.w, cc.y)) : kNoArea;
       }
       __syncwarp();
-      unsigned long long d0 = 0ull, d1 = 0ull;
-      if (r0 < s1) d0 = (unsigned long long)mask_row_bits_part<ZERO_SUP, kPart>(
-                            a0, __fmul_rn(__fsub_rn(a0.z, a0.x), __fsub_rn(a0.w, a0.y)), cbox, carea, thr_up) << (part * kPart);
-      if (r1 < s1) d1 = (unsigned long long)mask_row_bits_part<ZERO_SUP, kPart>(
-                            a1, __fmul_rn(__fsub_rn(a1.z, a1.x), __fsub_rn(a1.w, a1.y)), cbox, carea, thr_up) << (part * kPart);
-      if (cb == rb) {                                            // diagonal tile: only later boxes (j > row)
+      unsigned long long d0 = 0ull, d1 = 0ull;                    // (rows past the class end hold kNoBox: no bits)
+      if constexpr (ZERO_SUP) {
+        d0 = (unsigned long long)mask_row_bits_part<true, kPart>(
+                 a0, __fmul_rn(__fsub_rn(a0.z, a0.x), __fsub_rn(a0.w, a0.y)), cbox, carea, thr_up) << (part * kPart);
+        if (need1) d1 = (unsigned long long)mask_row_bits_part<true, kPart>(
+                 a1, __fmul_rn(__fsub_rn(a1.z, a1.x), __fsub_rn(a1.w, a1.y)), cbox, carea, thr_up) << (part * kPart);
+        if (r0 >= c.s1) d0 = 0ull;
+        if (r1 >= c.s1) d1 = 0ull;
+      } else {
+        unsigned b0, b1;
+        if (need1) mask_rows2_part<kPart, true>(a0, a1, cbox, carea, thr_up, b0, b1);
+        else mask_rows2_part<kPart, false>(a0, a1, cbox, carea, thr_up, b0, b1);
+        d0 = (unsigned long long)b0 << (part * kPart);
+        d1 = (unsigned long long)b1 << (part * kPart);
+      }
+      if (diag) {                                                // only later boxes (column > row)
         d0 &= ~((2ull << lane) - 1ull);
         d1 &= ~((2ull << (lane + 32)) - 1ull);
       }
-      if (d0) atomicOr(&tmask[(size_t)tile * kNmsTile + lane], d0);
-      if (d1) atomicOr(&tmask[(size_t)tile * kNmsTile + lane + 32], d1);
+      if (d0) atomicOr(&tmask[(size_t)tile_g * kNmsTile + lane], d0);
+      if (d1) atomicOr(&tmask[(size_t)tile_g * kNmsTile + lane + 32], d1);
     }
     __syncthreads();
-    if (k == rank) { B200DET_STAMP_NOSYNC(10); B200DET_NOTE_IF(blockIdx.x == 0 && blockIdx.y == 0, 12, W); B200DET_NOTE_IF(blockIdx.x == 0 && blockIdx.y == 0, 13, n_big); }
-    if (warp == 0) {
+    if (j0 == 0) { B200DET_STAMP_NOSYNC(10); B200DET_NOTE_IF(blockIdx.x == 0 && blockIdx.y == 0, 12, tiles); B200DET_NOTE_IF(blockIdx.x == 0 && blockIdx.y == 0, 13, cnt); }
+    for (int j = warp; j < cnt; j += kClassWarps) {              // greedy pass, one warp per class
+      const ClassSeg c = my_class(j0 + j);
+      const unsigned long long* buf = tmask + (size_t)s_toff[j] * kNmsTile;
       unsigned long long myrem = 0ull;                           // lane w: removed bits of the class's block w
       int tile = 0;
-      for (int rb = 0; rb < W; ++rb) {
-        const unsigned long long* diag = tmask + (size_t)tile * kNmsTile;
-        const int rows = min(kNmsTile, s1 - s0 - rb * kNmsTile);
+      for (int rb = 0; rb < c.W; ++rb) {
+        const unsigned long long* dg = buf + (size_t)tile * kNmsTile;
+        const int rows = min(kNmsTile, c.s1 - c.s0 - rb * kNmsTile);
         const unsigned long long valid = rows == kNmsTile ? ~0ull : ((1ull << rows) - 1ull);
-        const unsigned long long keep = resolve_block(shfl64(myrem, rb), valid, diag[lane], diag[lane + 32], lane);
+        const unsigned long long keep = resolve_block<64>(shfl64(myrem, rb), valid, dg[lane], dg[lane + 32], lane);
         const bool k0 = (keep >> lane) & 1ull, k1 = (keep >> (lane + 32)) & 1ull;
-        if (k0) keep_rank(rank_of(s0 + rb * kNmsTile + lane));
-        if (k1) keep_rank(rank_of(s0 + rb * kNmsTile + lane + 32));
-        for (int cb = rb + 1; cb < W; ++cb) {
-          const unsigned long long* col = tmask + (size_t)(tile + cb - rb) * kNmsTile;
+        if (k0) keep_rank(rank_of(c.s0 + rb * kNmsTile + lane));
+        if (k1) keep_rank(rank_of(c.s0 + rb * kNmsTile + lane + 32));
+        for (int cb = rb + 1; cb < c.W; ++cb) {
+          const unsigned long long* col = buf + (size_t)(tile + cb - rb) * kNmsTile;
           const unsigned long long v = warp_or64((k0 ? col[lane] : 0ull) | (k1 ? col[lane + 32] : 0ull));
           if (lane == cb) myrem |= v;
         }
-        tile += W - rb;
+        tile += c.W - rb;
       }
     }
-    __syncthreads();
-    if (k == rank) B200DET_STAMP_NOSYNC(11);
+    __syncthreads();                                             // the tile buffer and s_toff are free again
+    if (j0 == 0) { B200DET_STAMP_NOSYNC(11); }
+    j0 += cnt;
   }
   B200DET_STAMP_NOSYNC(14);
-
-  // 2b. classes of at most 64 boxes: one warp each, a single diagonal tile, nothing stored
-  for (int sg = rank * kClassWarps + warp; sg < n_seg; sg += kClassCluster * kClassWarps) {
-    const int s0 = seg[sg], s1 = sg + 1 < n_seg ? (int)seg[sg + 1] : n;
-    if (s1 - s0 > kNmsTile) continue;
-    const int r0 = s0 + lane, r1 = r0 + 32;
-    const bool ok0 = r0 < s1, ok1 = r1 < s1;
-    const float4 a0 = load_box(r0, s1), a1 = load_box(r1, s1);
-    stage_cols(a0, a1, ok0, ok1);
-    unsigned long long d0 = 0ull, d1 = 0ull;
-    if (ok0) d0 = mask_row_bits<ZERO_SUP>(a0, carea[lane], 0, cbox, carea, nullptr, thr_up, false);
-    if (ok1) d1 = mask_row_bits<ZERO_SUP>(a1, carea[lane + 32], 0, cbox, carea, nullptr, thr_up, false);
-    d0 &= ~((2ull << lane) - 1ull);
-    d1 &= ~((2ull << (lane + 32)) - 1ull);
-    const int rows = s1 - s0;
-    const unsigned long long valid = rows == kNmsTile ? ~0ull : ((1ull << rows) - 1ull);
-    const unsigned long long keep = resolve_block(0ull, valid, d0, d1, lane);
-    if ((keep >> lane) & 1ull) keep_rank(rank_of(r0));
-    if ((keep >> (lane + 32)) & 1ull) keep_rank(rank_of(r1));
-  }
   cluster.sync();                                                // every kept rank has landed in CTA 0
   B200DET_STAMP(4);
   if (rank != 0) return;

@@ -17,4 +17,11 @@ t = list(buf)
 names = ["keys", "sort", "segments", "class warps", "write"]
 print(" ".join(f"{n} +{(t[i + 1] - t[i]) / 1965:.1f}us" for i, n in enumerate(names)), "segments", t[8])
 if t[10]:
-    print(f"first big class of CTA 0: tiles evaluated +{(t[10] - t[3]) / 1965:.1f}us greedy +{(t[11] - t[10]) / 1965:.1f}us (W = {t[12]} blocks, {t[13]} big classes in the image); all big classes done +{(t[14] - t[3]) / 1965:.1f}us, small classes +{(t[4] - t[14]) / 1965:.1f}us")
+    print(f"first batch of CTA 0: tiles evaluated +{(t[10] - t[3]) / 1965:.1f}us greedy +{(t[11] - t[10]) / 1965:.1f}us "
+          f"({t[12]} tiles of {t[13]} classes); all batches done +{(t[14] - t[3]) / 1965:.1f}us")
+fn = lib.b200det_debug_read_trace_nms
+fn.argtypes = [C.c_void_p, C.c_int]
+fn(buf, 64)
+t = list(buf)
+names = ["threshold + rank", "bin starts", "placement", "rank in bin", "gather", "nms boxes"]
+print("nms_prepare_kernel, image 0: " + " ".join(f"{n} +{(t[31 + i] - t[30 + i]) / 1965:.1f}us" for i, n in enumerate(names)))

@@ -280,3 +280,37 @@ def test_every_dispatcher_op_has_a_cuda_kernel_and_a_fake_shape_function():
         r = torch.ops.b200det.assign_loss_fused(x[2], x[1], W.STRIDES, [-1.0] * 5, [64.0] * 5, gt, lab, 0, 1.5, None, None,
                                                 [torch.empty(1, device=dev)] * 5)
         assert r[4].shape == (2,) and len(r[8]) == 5 and r[9].shape == (5,)
+
+
+def test_iou_threshold_midpoint_test_equals_the_rounded_division():
+    """csrc/nms_body.cuh iou_reaches(): `fl32(inter / uni) >= thr_up` (torchvision's nms_kernel_impl expression as the
+    kernels used to evaluate it) is the same predicate as `double(inter) > mid * double(uni)` with mid the midpoint of
+    thr_up and the float below it.  Checked on random pairs and on pairs built to sit within a few ulps of the
+    threshold, for several thresholds including the smallest one (nms_thr = 0)."""
+    rng = np.random.default_rng(7)
+    for thr in (0.6, 0.5, 0.3, 0.05, 0.999, 1.0 / 3.0, 0.0, 1.5):
+        f = np.float32(thr)
+        if not float(f) > thr:
+            f = np.nextafter(f, np.float32(np.inf), dtype=np.float32)
+        below = (f.view(np.int32) - np.int32(1)).view(np.float32)
+        mid = 0.5 * (np.float64(below) + np.float64(f))
+        uni = np.exp(rng.uniform(-3, 12, 400000)).astype(np.float32)
+        near = (uni.astype(np.float64) * float(f)).astype(np.float32)
+        steps = rng.integers(-3, 4, near.shape)
+        for _ in range(3):                                  # walk a few ulps either side of thr_up * uni
+            near = np.where(steps > 0, np.nextafter(near, np.float32(np.inf)), np.where(steps < 0, np.nextafter(near, np.float32(-np.inf)), near)).astype(np.float32)
+            steps = steps - np.sign(steps)
+        inter = np.concatenate([near, (uni * rng.uniform(0, 1, uni.shape)).astype(np.float32)])
+        uni2 = np.concatenate([uni, uni])
+        special_i = np.array([0, 0, 1, np.inf, np.inf, np.nan, 1, 0, 1e-45], np.float32)
+        special_u = np.array([0, 1, 0, np.inf, 1, 1, np.nan, np.inf, 1e-45], np.float32)
+        inter = np.concatenate([inter, special_i])
+        uni2 = np.concatenate([uni2, special_u])
+        with np.errstate(all="ignore"):
+            ref = (inter / uni2).astype(np.float32) >= f
+            got = inter.astype(np.float64) > mid * uni2.astype(np.float64)
+        # 1 / 0 = inf reaches every threshold in the division form; a positive intersection with an empty union cannot
+        # come out of two overlapping boxes (uni >= the larger area >= inter > 0), so that pair is left out
+        keep = ~((uni2 == 0) & (inter > 0))
+        assert np.array_equal(ref[keep], got[keep]), thr
+        assert ref[: near.size].any() and not ref[: near.size].all()
