@@ -331,7 +331,7 @@ nms_scan_smem_kernel(const CandSet set, const int wblocks, const int cap_pad,
         keep = ~cur & valid;                                 // empty diagonal tile
       } else {
         const unsigned long long* diag = sm + col_off(rb) + rb * kNmsTile;
-        keep = resolve_block<64>(cur, valid, diag[lane], diag[lane + 32], lane);
+        keep = resolve_block(cur, valid, diag[lane], diag[lane + 32], lane);
       }
       if (lane == 0) keepw[rb] = keep;
       const bool k0 = (keep >> lane) & 1ull, k1 = (keep >> (lane + 32)) & 1ull;
@@ -435,7 +435,7 @@ nms_scan_ring_kernel(const CandSet set, const int wblocks, const int cap_pad,
     const int rows = min(kNmsTile, n - rb * kNmsTile);
     const unsigned long long valid = rows == kNmsTile ? ~0ull : ((1ull << rows) - 1ull);
     if (warp == 0) {
-      const unsigned long long keep = resolve_block<64>(removed[rb], valid, chunk[lane], chunk[lane + 32], lane);
+      const unsigned long long keep = resolve_block(removed[rb], valid, chunk[lane], chunk[lane + 32], lane);
       if (lane == 0) s_keep = keep;
     }
     __syncthreads();

@@ -176,27 +176,38 @@ __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int s
 // held lane-per-row (d0: row lane, d1: row lane+32).  If no still-alive row suppresses another
 // still-alive row (one warp OR-reduction) all alive rows are kept at once; otherwise the 64 rows
 // are walked serially out of registers (shuffles), the greedy rule of torchvision's nms kernel.
-// UNROLL = 64 turns the bit tests of the walk into constants (measured on the dense path: 1 000 crowded candidates
-// x 16 images 60.9 -> 54.8 us); the fused kernel, where the walk is rare, keeps the compact loop.
-template <int UNROLL = 8>
+//
+// The walk is a dependency chain, so it is written for the shortest one: row i only matters through the boxes AFTER
+// it (bits > i; lower bits are decided already), so bit i of the removed set is final when step i reads it and the
+// kept rows are simply the valid rows not removed at the end; rows past `valid` are zeroed before the walk; rows
+// 32-63 only touch the high word.  What is left per step is one bit test and one predicated OR (~15 cycles; the
+// shuffles that fetch the rows do not depend on the chain and run ahead) — the straightforward loop (alive flag from
+// valid and removed, select, OR, keep mask) was four dependent instructions and ~39 cycles per row, 1.3 us per block.
+// (Walking only the kept rows — next = lowest row neither removed nor visited — was measured and is SLOWER: its
+// shuffle depends on the previous step; 1 000 crowded candidates x 16 images: 80.6 vs 68.6 us.)
 __device__ __forceinline__ unsigned long long resolve_block(const unsigned long long cur, const unsigned long long valid,
-                                                            const unsigned long long d0, const unsigned long long d1,
-                                                            const int lane) {
+                                                            unsigned long long d0, unsigned long long d1, const int lane) {
+  d0 = ((valid >> lane) & 1ull) ? d0 & ~((2ull << lane) - 1ull) : 0ull;           // later boxes of valid rows only
+  d1 = ((valid >> (lane + 32)) & 1ull) ? d1 & ~((2ull << (lane + 32)) - 1ull) : 0ull;
   const bool a0 = !((cur >> lane) & 1ull), a1 = !((cur >> (lane + 32)) & 1ull);
   const unsigned long long S = warp_or64((a0 ? d0 : 0ull) | (a1 ? d1 : 0ull));
   if (((S & ~cur) & valid) == 0ull) return ~cur & valid;
-  // (Walking only the kept rows — next = lowest row neither removed nor visited — was measured and is SLOWER: its
-  // shuffle depends on the previous step, ~40 cycles each, while here the 64 row fetches are independent of the
-  // chain and pipeline; 1 000 crowded candidates x 16 images: 80.6 vs 68.6 us.)
-  unsigned long long c = cur, keep = 0ull;
-#pragma unroll(UNROLL)
-  for (int i = 0; i < kNmsTile; ++i) {
-    const unsigned long long di = shfl64(i < 32 ? d0 : d1, i & 31);
-    const bool alive = ((valid >> i) & 1ull) && !((c >> i) & 1ull);
-    keep |= alive ? (1ull << i) : 0ull;
-    c |= alive ? di : 0ull;
+  unsigned c_lo = (unsigned)cur, c_hi = (unsigned)(cur >> 32);
+  const unsigned d0_lo = (unsigned)d0, d0_hi = (unsigned)(d0 >> 32), d1_hi = (unsigned)(d1 >> 32);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const unsigned r_lo = __shfl_sync(0xffffffffu, d0_lo, i), r_hi = __shfl_sync(0xffffffffu, d0_hi, i);
+    if (!(c_lo & (1u << i))) {
+      c_lo |= r_lo;
+      c_hi |= r_hi;
+    }
   }
-  return keep;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const unsigned r_hi = __shfl_sync(0xffffffffu, d1_hi, i);
+    if (!(c_hi & (1u << i))) c_hi |= r_hi;
+  }
+  return ~(((unsigned long long)c_hi << 32) | c_lo) & valid;
 }
 
 // gather + (optional) clip + store of one kept row

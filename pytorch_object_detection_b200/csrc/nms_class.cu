@@ -31,6 +31,8 @@ constexpr int kClassThreads = 1024;
 constexpr int kClassWarps = kClassThreads / 32;
 constexpr int kClassMaxSeg = 1024;            // boxes of one class handled by a warp (16 blocks of 64)
 constexpr int kRankBits = 13;                 // rank < 8192 = B200DET_MAX_BOX
+constexpr int kEarly = 8;                     // greedy passes that may follow their class's pair tests row by row
+constexpr int kBoxBudget = 2048;              // boxes of one batch of classes in shared memory
 constexpr int kOrderMax = 256;                // classes dealt to the CTAs in order of size up to this many
 constexpr int kDenseClasses = 256;            // class ids below this take the table-driven stable split
 constexpr int kTileBudget = (kClassMaxSeg / 64) * (kClassMaxSeg / 64 + 1) / 2;   // 136 tiles of 64 x 64 bits in shared memory
@@ -60,6 +62,11 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
   __shared__ int s_pre[B200DET_MAX_BOX / 64 + 1];
   __shared__ unsigned short s_cstart[kDenseClasses];             // first slot of a class (dense-id path)
   __shared__ unsigned short s_toff[kTileBudget + 1];            // first tile of the batch's classes
+  __shared__ unsigned short s_boff[kTileBudget + 1];            // first box of the batch's classes in sbox
+  __shared__ unsigned short s_s0[kTileBudget];                  // where the class starts in keys[]
+  __shared__ unsigned short s_roff[kTileBudget];                // first tile row of the batch's classes in s_done
+  __shared__ int s_done[kTileBudget];                           // units of pair tests finished, per tile row of a class
+  __shared__ int s_queue[3];                                    // next unit, next class to be resolved, early passes
   __shared__ unsigned short s_ord[kOrderMax];                   // classes by size, largest first
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   cg::cluster_group cluster = cg::this_cluster();
@@ -72,22 +79,22 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
   B200DET_STAMP(0);
   int n2 = 1;
   while (n2 < n) n2 <<= 1;
-  // shared memory: keys [n2] u32 | segment starts [n2] u16 | keep bitmap [n2 / 32] u32 | per-warp column staging
-  // | tile bits of the class being resolved cooperatively
+  // shared memory: keys [n2] u32 | segment starts [n2] u16 | keep bitmap [n2 / 32] u32 | boxes and areas of the
+  // classes being resolved | their tile bits
   unsigned* keys = reinterpret_cast<unsigned*>(smem_raw);
   unsigned short* seg = reinterpret_cast<unsigned short*>(keys + n2);
   unsigned* keepbits = reinterpret_cast<unsigned*>(seg + n2);
   const int kwords = (n2 + 31) / 32;
   float4* cbox_all = reinterpret_cast<float4*>(smem_raw + (((size_t)n2 * 6 + (size_t)kwords * 4 + 15) / 16) * 16);
-  float* carea_all = reinterpret_cast<float*>(cbox_all + kClassWarps * kNmsTile);
-  unsigned long long* tmask = reinterpret_cast<unsigned long long*>(carea_all + kClassWarps * kNmsTile);   // [136 tiles][64]
+  float* carea_all = reinterpret_cast<float*>(cbox_all + kBoxBudget + kNmsTile);
+  unsigned long long* tmask = reinterpret_cast<unsigned long long*>(carea_all + kBoxBudget + kNmsTile);   // [136 tiles][64]
   const size_t o0 = (size_t)b * set.cap;
   const size_t q0 = (size_t)b * out.stride;
 
   // ---- 1. (class, rank) keys, sorted: one contiguous score-ordered segment per class -----------------------
   // The candidate list arrives in score order, so this is a STABLE split by class.
   // (a) Class ids below kDenseClasses (COCO, VOC): warp w takes a contiguous run of 32-key groups; in a group the
-  //     lanes of one class find each other with match.any, and a per-warp count table [warp][class] gives every key
+  //     lanes of one class find each other with ballots on the id's bits, and a per-warp count table [warp][class] gives every key
   //     its position among the warp's keys of its class.  One pass down the table's columns turns the counts into
   //     offsets, one scan over the classes gives the class starts (= the segments) — ~2 us for 5 000 candidates, and
   //     nothing is ranked or compared.
@@ -96,11 +103,12 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
   //     and the 8 192-key bitonic network for class ids it cannot bin.
   static_assert(kClassThreads == kHistThreads, "the class histogram is scanned by 1024 threads");
   unsigned* chist = reinterpret_cast<unsigned*>(tmask);                 // [kHistBins] (tmask holds 136 x 64 x 8 bytes)
-  unsigned* tmpk = reinterpret_cast<unsigned*>(cbox_all);               // [n] (cbox_all holds 32 x 64 x 16 bytes)
+  unsigned* tmpk = reinterpret_cast<unsigned*>(cbox_all);               // [n] (cbox_all holds 2112 x 16 bytes)
   unsigned short* wcnt = reinterpret_cast<unsigned short*>(tmask);      // [kClassWarps][kDenseClasses]
   static_assert((size_t)(kClassMaxSeg / kNmsTile) * (kClassMaxSeg / kNmsTile + 1) / 2 * kNmsTile * 8 >= (size_t)kHistBins * 4,
                 "class histogram aliases the tile bits");
-  static_assert((size_t)kClassWarps * kNmsTile * sizeof(float4) >= (size_t)B200DET_MAX_BOX * 4, "key scratch aliases the column staging");
+  static_assert((size_t)(kBoxBudget + kNmsTile) * sizeof(float4) >= (size_t)B200DET_MAX_BOX * 4, "key scratch aliases the staged boxes");
+  static_assert(kBoxBudget >= kClassMaxSeg && (kBoxBudget + kNmsTile) % 2 == 0, "a class alone fits; the tile bits stay 8-byte aligned");
   static_assert(kClassWarps * kDenseClasses * 2 == kClassThreads * 16, "one uint4 per thread clears the count table");
   reinterpret_cast<uint4*>(wcnt)[tid] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < kwords; i += kClassThreads) keepbits[i] = 0u;
@@ -125,7 +133,15 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
     const bool ok = in && c >= 0 && c < kDenseClasses;
     sparse = sparse || (in && !ok);
     cmax = cmax || (in && (c < 0 || c >= (1 << (32 - kRankBits - 1))));
-    const unsigned peers = __match_any_sync(0xffffffffu, ok ? c : kDenseClasses + lane);
+    // lanes of the same class: 8 ballots on the bits of the id (match.any takes one pass per distinct value: the five
+    // groups of a warp cost ~4 us of this kernel)
+    unsigned peers = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+    for (int bit = 0; bit < 8; ++bit) {
+      const unsigned v = __ballot_sync(0xffffffffu, (c >> bit) & 1);
+      peers &= ((c >> bit) & 1) ? v : ~v;
+    }
+    static_assert(kDenseClasses == 256, "eight bits tell the dense class ids apart");
     const int r = __popc(peers & ((1u << lane) - 1u));
     const unsigned short base = ok ? wrow[c] : (unsigned short)0;
     __syncwarp();
@@ -237,27 +253,22 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
   }
   if (bad_class || longest > (float)kClassMaxSeg) return;        // left to the dense path (mode stays vanilla)
   cluster.sync();                                                // CTA 0's keep bitmap is clear; every CTA runs
-  unsigned* image_keep = cluster.map_shared_rank(keepbits, 0);   // kept ranks meet in CTA 0 (32-bit atomicOr, DSMEM)
+  // kept ranks go to the bitmap of EVERY CTA of the cluster (32-bit reductions through DSMEM), so that after the
+  // cluster barrier each of them can write a slice of the output
 
   B200DET_STAMP(3);
   // ---- 2. every class on its own ---------------------------------------------------------------------------------
-  float4* cbox = cbox_all + warp * kNmsTile;
-  float* carea = carea_all + warp * kNmsTile;
-  const float4 kNoBox = make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);   // overlaps nothing
-  const float kNoArea = __int_as_float(0x7fc00000);                                             // NaN: never suppresses
-  auto load_box = [&](const int pos, const int end) {
-    return pos < end ? reinterpret_cast<const float4*>(set.box)[o0 + (keys[pos] & ((1u << kRankBits) - 1u))] : kNoBox;
-  };
   auto rank_of = [&](const int pos) { return keys[pos] & ((1u << kRankBits) - 1u); };
-  auto keep_rank = [&](const unsigned r) { atomicOr(image_keep + (r >> 5), 1u << (r & 31)); };
+  auto keep_rank = [&](const unsigned r) {                      // bit r of the keep bitmap of every CTA of the cluster
+    const unsigned word = (unsigned)__cvta_generic_to_shared(keepbits + (r >> 5));
+#pragma unroll
+    for (int t = 0; t < kClassCluster; ++t) {
+      unsigned remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(word), "r"(t));
+      asm volatile("red.relaxed.cluster.shared::cluster.or.b32 [%0], %1;" ::"r"(remote), "r"(1u << (r & 31)) : "memory");
+    }
+  };
 
-  // The classes are dealt round-robin to the cluster's CTAs.  A CTA takes its classes in batches whose tiles
-  // (64 x 64 blocks of the upper triangle, one for a class of <= 64 boxes) fit the tile buffer — for 5 000 candidates
-  // of 80 classes all ten classes of a CTA are one batch — and per batch
-  //   * ALL warps evaluate the batch's tiles into shared memory, a (tile, 16-column part) unit at a time: a single
-  //     warp needs ~10 us of dependent issue for a whole tile, so the pair tests are spread as thin as they go;
-  //   * then one warp per class runs the greedy pass over the stored bits (a serial chain), the classes in parallel.
-  constexpr int kPart = 16, kParts = kNmsTile / kPart;
   // Dealing: the classes in order of size, largest first, laid out boustrophedon over the CTAs (0..7, 7..0, ...), so
   // every CTA gets a like share of the pair tests (plain round-robin left the slowest CTA of a cluster ~13 us behind
   // the first on 5 000 candidates of 80 classes).  The order costs one n_seg-long count per class, so it is taken up
@@ -273,15 +284,8 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
     s_ord[before] = (unsigned short)tid;
   }
   __syncthreads();
-  struct ClassSeg { int s0, s1, W; };
-  auto my_class = [&](const int j) {                            // the j-th class of this CTA
-    const int sg = ordered ? (int)s_ord[j * kClassCluster + ((j & 1) ? kClassCluster - 1 - rank : rank)]
-                           : rank + j * kClassCluster;
-    ClassSeg c;
-    c.s0 = seg[sg];
-    c.s1 = sg + 1 < n_seg ? (int)seg[sg + 1] : n;
-    c.W = (c.s1 - c.s0 + kNmsTile - 1) / kNmsTile;              // 1 .. 16 blocks
-    return c;
+  auto my_segment = [&](const int j) {                          // the j-th class of this CTA
+    return ordered ? (int)s_ord[j * kClassCluster + ((j & 1) ? kClassCluster - 1 - rank : rank)] : rank + j * kClassCluster;
   };
   int my_n;
   {
@@ -289,98 +293,189 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
     const int col = (ordered && (rows & 1)) ? kClassCluster - 1 - rank : rank;
     my_n = rows + (col < left ? 1 : 0);
   }
+
+  // A CTA takes its classes in batches whose boxes and tiles (64 x 64 blocks of the upper triangle, one for a class
+  // of <= 64 boxes) fit shared memory — for 5 000 candidates of 80 classes all ten classes of a CTA are one batch.
+  // Per batch the boxes are gathered into shared memory once, class after class; then the warps serve two queues:
+  //   * pair tests, a (tile, 16-column part) unit at a time — a single warp needs ~10 us of dependent issue for a
+  //     whole tile, so they are spread as thin as they go; the units of the largest class come first;
+  //   * greedy passes, one warp per class over the stored bits (a serial chain of up to ~8 us), taken as soon as the
+  //     last unit of the class has been counted in, so the long chains run beside the pair tests of the other classes.
+  constexpr int kPart = 16, kParts = kNmsTile / kPart;
+  float4* sbox = cbox_all;                                       // [kBoxBudget + 64] the batch's boxes, class after class
+  float* sarea = carea_all;                                      // [kBoxBudget + 64]
   for (int j0 = 0; j0 < my_n;) {
-    int cnt = 0, tiles = 0;                                      // the batch: classes j0 .. j0 + cnt - 1
+    int cnt = 0, tiles = 0, boxes = 0, rows = 0;                 // the batch: classes j0 .. j0 + cnt - 1
     while (j0 + cnt < my_n && cnt < kTileBudget) {
-      const int W = my_class(j0 + cnt).W;
+      const int sg = my_segment(j0 + cnt);
+      const int s0 = seg[sg], size = (sg + 1 < n_seg ? (int)seg[sg + 1] : n) - s0;
+      const int W = (size + kNmsTile - 1) / kNmsTile;            // 1 .. 16 blocks
       const int t = W * (W + 1) / 2;
-      if (tiles + t > kTileBudget) break;                        // (a class alone always fits: W <= 16)
-      if (tid == 0) s_toff[cnt] = (unsigned short)tiles;
+      if (tiles + t > kTileBudget || boxes + size > kBoxBudget) break;   // (a class alone always fits)
+      if (tid == 0) {
+        s_toff[cnt] = (unsigned short)tiles;
+        s_boff[cnt] = (unsigned short)boxes;
+        s_s0[cnt] = (unsigned short)s0;
+        s_roff[cnt] = (unsigned short)rows;
+      }
       tiles += t;
+      boxes += size;
+      rows += W;
       ++cnt;
     }
-    if (tid == 0) s_toff[cnt] = (unsigned short)tiles;
+    if (tid == 0) {
+      s_toff[cnt] = (unsigned short)tiles;
+      s_boff[cnt] = (unsigned short)boxes;
+      s_queue[0] = 0;                                            // next unit
+      s_queue[1] = 0;                                            // next class to be resolved
+      s_queue[2] = 0;                                            // greedy passes running ahead of their class's tiles
+    }
+    for (int i = tid; i < rows; i += kClassThreads) s_done[i] = 0;
     for (int i = tid; i < tiles * kNmsTile; i += kClassThreads) tmask[i] = 0ull;
     __syncthreads();
-    for (int unit = warp; unit < tiles * kParts; unit += kClassWarps) {
-      const int tile_g = unit / kParts, part = unit - tile_g * kParts;
-      int lo = 0, hi = cnt;                                      // s_toff[lo] <= tile_g < s_toff[hi]
+    // class of the batch that holds box / tile number v of the batch (offsets in `off`)
+    auto class_of = [&](const unsigned short* off, const int v) {
+      int lo = 0, hi = cnt;                                      // off[lo] <= v < off[hi]
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if ((int)s_toff[mid] <= tile_g) lo = mid; else hi = mid;
+        if ((int)off[mid] <= v) lo = mid; else hi = mid;
       }
-      const ClassSeg c = my_class(j0 + lo);
-      int rb = 0, rem = tile_g - (int)s_toff[lo];
-      while (rem >= c.W - rb) { rem -= c.W - rb; ++rb; }          // row-major upper triangle
-      const int cb = rb + rem;
-      const int col0 = c.s0 + cb * kNmsTile + part * kPart;
-      if (col0 >= c.s1) continue;                                // no column in this part
-      const bool diag = cb == rb;
-      const int r0 = c.s0 + rb * kNmsTile + lane, r1 = r0 + 32;
-      const bool need1 = !(diag && part < 2);                    // diagonal tile: rows 32-63 only see columns > 32
-      const float4 a0 = load_box(r0, c.s1), a1 = need1 ? load_box(r1, c.s1) : kNoBox;
-      const float4 cc = lane < kPart ? load_box(col0 + lane, c.s1) : kNoBox;   // (lanes 0-15 stage the columns)
-      __syncwarp();
-      if (lane < kPart) {
-        cbox[lane] = cc;
-        carea[lane] = col0 + lane < c.s1 ? __fmul_rn(__fsub_rn(cc.z, cc.x), __fsub_rn(cc.w, cc.y)) : kNoArea;
-      }
-      __syncwarp();
-      unsigned long long d0 = 0ull, d1 = 0ull;                    // (rows past the class end hold kNoBox: no bits)
-      if constexpr (ZERO_SUP) {
-        d0 = (unsigned long long)mask_row_bits_part<true, kPart>(
-                 a0, __fmul_rn(__fsub_rn(a0.z, a0.x), __fsub_rn(a0.w, a0.y)), cbox, carea, thr_up) << (part * kPart);
-        if (need1) d1 = (unsigned long long)mask_row_bits_part<true, kPart>(
-                 a1, __fmul_rn(__fsub_rn(a1.z, a1.x), __fsub_rn(a1.w, a1.y)), cbox, carea, thr_up) << (part * kPart);
-        if (r0 >= c.s1) d0 = 0ull;
-        if (r1 >= c.s1) d1 = 0ull;
-      } else {
-        unsigned b0, b1;
-        if (need1) mask_rows2_part<kPart, true>(a0, a1, cbox, carea, thr_up, b0, b1);
-        else mask_rows2_part<kPart, false>(a0, a1, cbox, carea, thr_up, b0, b1);
-        d0 = (unsigned long long)b0 << (part * kPart);
-        d1 = (unsigned long long)b1 << (part * kPart);
-      }
-      if (diag) {                                                // only later boxes (column > row)
-        d0 &= ~((2ull << lane) - 1ull);
-        d1 &= ~((2ull << (lane + 32)) - 1ull);
-      }
-      if (d0) atomicOr(&tmask[(size_t)tile_g * kNmsTile + lane], d0);
-      if (d1) atomicOr(&tmask[(size_t)tile_g * kNmsTile + lane + 32], d1);
+      return lo;
+    };
+    for (int i = tid; i < boxes; i += kClassThreads) {
+      const int j = class_of(s_boff, i);
+      const float4 v = reinterpret_cast<const float4*>(set.box)[o0 + rank_of((int)s_s0[j] + i - (int)s_boff[j])];
+      sbox[i] = v;
+      sarea[i] = __fmul_rn(__fsub_rn(v.z, v.x), __fsub_rn(v.w, v.y));
     }
     __syncthreads();
-    if (j0 == 0) { B200DET_STAMP_NOSYNC(10); B200DET_NOTE_IF(blockIdx.x == 0 && blockIdx.y == 0, 12, tiles); B200DET_NOTE_IF(blockIdx.x == 0 && blockIdx.y == 0, 13, cnt); }
-    for (int j = warp; j < cnt; j += kClassWarps) {              // greedy pass, one warp per class
-      const ClassSeg c = my_class(j0 + j);
-      const unsigned long long* buf = tmask + (size_t)s_toff[j] * kNmsTile;
-      unsigned long long myrem = 0ull;                           // lane w: removed bits of the class's block w
-      int tile = 0;
-      for (int rb = 0; rb < c.W; ++rb) {
-        const unsigned long long* dg = buf + (size_t)tile * kNmsTile;
-        const int rows = min(kNmsTile, c.s1 - c.s0 - rb * kNmsTile);
-        const unsigned long long valid = rows == kNmsTile ? ~0ull : ((1ull << rows) - 1ull);
-        const unsigned long long keep = resolve_block<64>(shfl64(myrem, rb), valid, dg[lane], dg[lane + 32], lane);
-        const bool k0 = (keep >> lane) & 1ull, k1 = (keep >> (lane + 32)) & 1ull;
-        if (k0) keep_rank(rank_of(c.s0 + rb * kNmsTile + lane));
-        if (k1) keep_rank(rank_of(c.s0 + rb * kNmsTile + lane + 32));
-        for (int cb = rb + 1; cb < c.W; ++cb) {
-          const unsigned long long* col = buf + (size_t)(tile + cb - rb) * kNmsTile;
-          const unsigned long long v = warp_or64((k0 ? col[lane] : 0ull) | (k1 ? col[lane + 32] : 0ull));
-          if (lane == cb) myrem |= v;
+    const int units = tiles * kParts;
+    volatile int* queue = s_queue;
+    volatile int* done = s_done;
+    for (;;) {
+      // (a) a class whose greedy pass can start and nobody has taken?  (Classes are handed out in order, the order of
+      //     their units.)  A class of up to two row blocks starts when all its tiles are complete.  A larger one
+      //     starts as soon as its FIRST tile row is and then follows the pair tests row by row — it is most of the
+      //     CTA's critical path: 28 tiles, then a 7 us chain — waiting where it catches up; at most kEarly such
+      //     passes at a time, so that the other warps keep the pair tests going.
+      int g = -1;
+      bool early = false;
+      if (lane == 0) {
+        const int next = queue[1];
+        if (next < cnt) {
+          const int size = (int)s_boff[next + 1] - (int)s_boff[next];
+          const int W = (size + kNmsTile - 1) / kNmsTile, r0 = s_roff[next];
+          bool ready = done[r0] == W * kParts;
+          early = W > 2;
+          if (!early && ready && W == 2) ready = done[r0 + 1] == kParts;
+          if (early && ready) ready = atomicAdd(&s_queue[2], 1) < kEarly || (atomicSub(&s_queue[2], 1), false);
+          if (ready) {
+            if (atomicCAS(&s_queue[1], next, next + 1) == next) g = next;
+            else if (early) atomicSub(&s_queue[2], 1);
+          }
         }
-        tile += c.W - rb;
       }
+      g = __shfl_sync(0xffffffffu, g, 0);
+      if (g >= 0) {
+        __threadfence_block();                                   // the bits counted in by done[g] are visible
+        B200DET_STAMP_ANY(lane == 0 && g == 0 && j0 == 0 && blockIdx.x == 0 && blockIdx.y == 0, 15);
+        B200DET_STAMP_ANY(lane == 0 && g == cnt - 1 && j0 == 0 && blockIdx.x == 0 && blockIdx.y == 0, 17);
+        const int s0 = s_s0[g], size = (int)s_boff[g + 1] - (int)s_boff[g];
+        const int W = (size + kNmsTile - 1) / kNmsTile, row0 = s_roff[g];
+        const unsigned long long* buf = tmask + (size_t)s_toff[g] * kNmsTile;
+        unsigned long long myrem = 0ull;                         // lane w: removed bits of the class's block w
+        int tile = 0;
+        for (int rb = 0; rb < W; ++rb) {
+          if (W > 2 && rb > 0) {                                 // the pair tests of this tile row
+            while (done[row0 + rb] != (W - rb) * kParts) __nanosleep(64);
+            __threadfence_block();
+          }
+          const unsigned long long* dg = buf + (size_t)tile * kNmsTile;
+          const int rows_here = min(kNmsTile, size - rb * kNmsTile);
+          const unsigned long long valid = rows_here == kNmsTile ? ~0ull : ((1ull << rows_here) - 1ull);
+          const unsigned long long keep = resolve_block(shfl64(myrem, rb), valid, dg[lane], dg[lane + 32], lane);
+          const bool k0 = (keep >> lane) & 1ull, k1 = (keep >> (lane + 32)) & 1ull;
+          if (k0) keep_rank(rank_of(s0 + rb * kNmsTile + lane));
+          if (k1) keep_rank(rank_of(s0 + rb * kNmsTile + lane + 32));
+          for (int cb = rb + 1; cb < W; ++cb) {
+            const unsigned long long* col = buf + (size_t)(tile + cb - rb) * kNmsTile;
+            const unsigned long long v = warp_or64((k0 ? col[lane] : 0ull) | (k1 ? col[lane + 32] : 0ull));
+            if (lane == cb) myrem |= v;
+          }
+          tile += W - rb;
+        }
+        if (W > 2 && lane == 0) atomicSub(&s_queue[2], 1);
+        B200DET_STAMP_ANY(lane == 0 && g == 0 && j0 == 0 && blockIdx.x == 0 && blockIdx.y == 0, 16);
+        B200DET_STAMP_ANY(lane == 0 && g == cnt - 1 && j0 == 0 && blockIdx.x == 0 && blockIdx.y == 0, 18);
+        continue;
+      }
+      // (b) a unit of pair tests
+      int unit = 0;
+      if (lane == 0) unit = queue[0] < units ? atomicAdd(&s_queue[0], 1) : units;
+      unit = __shfl_sync(0xffffffffu, unit, 0);
+      B200DET_STAMP_ANY(lane == 0 && unit == units - 1 && j0 == 0 && blockIdx.x == 0 && blockIdx.y == 0, 19);
+      B200DET_STAMP_ANY(lane == 0 && unit == 0 && j0 == 0 && blockIdx.x == 0 && blockIdx.y == 0, 20);
+      if (unit < units) {
+        const int tile_g = unit / kParts, part = unit - tile_g * kParts;
+        const int j = class_of(s_toff, tile_g);
+        const int b0 = s_boff[j], size = (int)s_boff[j + 1] - b0;
+        const int W = (size + kNmsTile - 1) / kNmsTile;
+        int rb = 0, rem = tile_g - (int)s_toff[j];
+        while (rem >= W - rb) { rem -= W - rb; ++rb; }            // row-major upper triangle
+        const int cb = rb + rem;
+        const int col0 = cb * kNmsTile + part * kPart;           // (positions inside the class)
+        if (col0 < size) {                                       // else: no column in this part
+          const bool diag = cb == rb;
+          const bool need1 = !(diag && part < 2);                // diagonal tile: rows 32-63 only see columns > 32
+          const int r0 = rb * kNmsTile + lane, r1 = r0 + 32;
+          // Rows and columns past the end of the class read the boxes that follow in shared memory (64 entries of
+          // slack behind the last class): row bits are cleared below, column bits beyond the class never reach a
+          // kept rank (the greedy pass masks every block with its valid rows).
+          const float4 a0 = sbox[b0 + r0], a1 = sbox[b0 + r1];
+          const float4* cbox = sbox + b0 + col0;
+          const float* carea = sarea + b0 + col0;
+          unsigned lo0, lo1 = 0u;
+          if constexpr (ZERO_SUP) {
+            lo0 = mask_row_bits_part<true, kPart>(a0, sarea[b0 + r0], cbox, carea, thr_up);
+            if (need1) lo1 = mask_row_bits_part<true, kPart>(a1, sarea[b0 + r1], cbox, carea, thr_up);
+          } else {
+            if (need1) mask_rows2_part<kPart, true>(a0, a1, cbox, carea, thr_up, lo0, lo1);
+            else mask_rows2_part<kPart, false>(a0, a1, cbox, carea, thr_up, lo0, lo1);
+          }
+          unsigned long long d0 = r0 < size ? (unsigned long long)lo0 << (part * kPart) : 0ull;
+          unsigned long long d1 = r1 < size ? (unsigned long long)lo1 << (part * kPart) : 0ull;
+          if (diag) {                                            // only later boxes (column > row)
+            d0 &= ~((2ull << lane) - 1ull);
+            d1 &= ~((2ull << (lane + 32)) - 1ull);
+          }
+          // the four parts of a word own 16 bits each: native 32-bit atomics on its halves
+          unsigned* w0 = reinterpret_cast<unsigned*>(tmask + (size_t)tile_g * kNmsTile + lane) + (part >> 1);
+          const unsigned h0 = (unsigned)(d0 >> ((part >> 1) * 32)), h1 = (unsigned)(d1 >> ((part >> 1) * 32));
+          if (h0) atomicOr(w0, h0);
+          if (h1) atomicOr(w0 + 64, h1);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();                                 // the unit's bits before its count
+          atomicAdd(&s_done[(int)s_roff[j] + rb], 1);
+        }
+        continue;
+      }
+      // (c) nothing to test: leave once every class has been taken, else wait for the units in flight
+      int left = 0;
+      if (lane == 0) left = queue[1] < cnt ? 1 : 0;
+      if (!__shfl_sync(0xffffffffu, left, 0)) break;
+      __nanosleep(100);
     }
-    __syncthreads();                                             // the tile buffer and s_toff are free again
-    if (j0 == 0) { B200DET_STAMP_NOSYNC(11); }
+    __syncthreads();                                             // the buffers and the batch tables are free again
+    if (j0 == 0) { B200DET_STAMP_NOSYNC(11); B200DET_NOTE_IF(blockIdx.x == 0 && blockIdx.y == 0, 12, tiles); B200DET_NOTE_IF(blockIdx.x == 0 && blockIdx.y == 0, 13, cnt); }
     j0 += cnt;
   }
   B200DET_STAMP_NOSYNC(14);
-  cluster.sync();                                                // every kept rank has landed in CTA 0
+  cluster.sync();                                                // every kept rank has landed in every CTA
   B200DET_STAMP(4);
-  if (rank != 0) return;
 
-  // ---- 3. kept candidates in score (rank) order -------------------------------------------------------------------
+  // ---- 3. kept candidates in score (rank) order: every CTA writes an eighth of the ranks ------------------------------
   const int w64 = (n + 63) / 64;
   int run = 0;
   for (int base = 0; base < w64; base += kClassThreads) {        // exclusive prefix of kept counts per 64-rank word
@@ -392,7 +487,9 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
     run += total;
   }
   __syncthreads();
-  for (int q = tid; q < n; q += kClassThreads) {
+  const int slice = (w64 + kClassCluster - 1) / kClassCluster * 64;
+  const int q_end = min(n, (rank + 1) * slice);
+  for (int q = rank * slice + tid; q < q_end; q += kClassThreads) {
     if (!((keepbits[q >> 5] >> (q & 31)) & 1u)) continue;
     const unsigned lo = keepbits[(q >> 6) * 2];
     const unsigned hi = (q >> 6) * 2 + 1 < kwords ? keepbits[(q >> 6) * 2 + 1] : 0u;
@@ -405,7 +502,7 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
 #ifdef B200DET_TRACE
   if (tid == 0 && blockIdx.x == 0) g_trace[8] = n_seg;
 #endif
-  if (tid == 0) {
+  if (tid == 0 && rank == 0) {
     out.count[b] = run;
     set.mode[b] = kModeDone;                                     // the dense kernels skip this image
   }
@@ -416,7 +513,7 @@ size_t class_smem_bytes(int cap) {
   while (n2 < cap) n2 <<= 1;
   const size_t head = (((size_t)n2 * 6 + (size_t)((n2 + 31) / 32) * 4 + 15) / 16) * 16;
   const size_t max_tiles = (size_t)(kClassMaxSeg / kNmsTile) * (kClassMaxSeg / kNmsTile + 1) / 2;
-  return head + (size_t)kClassWarps * kNmsTile * (sizeof(float4) + sizeof(float)) + max_tiles * kNmsTile * 8;
+  return head + (size_t)(kBoxBudget + kNmsTile) * (sizeof(float4) + sizeof(float)) + max_tiles * kNmsTile * 8;
 }
 
 }  // namespace

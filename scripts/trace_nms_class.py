@@ -16,9 +16,12 @@ fn(buf, 64)
 t = list(buf)
 names = ["keys", "sort", "segments", "class warps", "write"]
 print(" ".join(f"{n} +{(t[i + 1] - t[i]) / 1965:.1f}us" for i, n in enumerate(names)), "segments", t[8])
-if t[10]:
-    print(f"first batch of CTA 0: tiles evaluated +{(t[10] - t[3]) / 1965:.1f}us greedy +{(t[11] - t[10]) / 1965:.1f}us "
-          f"({t[12]} tiles of {t[13]} classes); all batches done +{(t[14] - t[3]) / 1965:.1f}us")
+if t[11]:
+    print(f"first batch of CTA 0 ({t[12]} tiles of {t[13]} classes): done +{(t[11] - t[3]) / 1965:.1f}us; all batches +{(t[14] - t[3]) / 1965:.1f}us")
+if t[15]:
+    rel = lambda i: (t[i] - t[3]) / 1965
+    print(f"  CTA 0: first unit taken at {rel(20):.1f}us, last unit taken at {rel(19):.1f}us; greedy pass of the largest class {rel(15):.1f} -> {rel(16):.1f}us, "
+          f"of the smallest {rel(17):.1f} -> {rel(18):.1f}us")
 fn = lib.b200det_debug_read_trace_nms
 fn.argtypes = [C.c_void_p, C.c_int]
 fn(buf, 64)

@@ -47,7 +47,7 @@ if fused:
     fn.argtypes = [C.c_void_p, C.c_int]
     fn(buf, 64)
     tt = list(buf)
-    if tt[20]:
-        labels = ["keys loaded + hist zeroed", "hist atomics", "scan", "threshold + slot ranges", "placement", "(rank + decode start ->) K2 sort stamp"]
-        pts = [tt[0], tt[20], tt[21], tt[22], tt[23], tt[24], tt[5]]
+    if tt[21]:
+        labels = ["keys loaded + counted", "scan", "threshold + slot ranges", "placement", "rank in bin"]
+        pts = [tt[0], tt[21], tt[22], tt[23], tt[24], tt[1]]
         print("select, histogram path:", "  ".join(f"{l} +{(b - a) / 1965:.2f}" for l, a, b in zip(labels, pts, pts[1:])))

@@ -161,6 +161,51 @@ def test_nms_matches_oracle_random(seed, n, ncls):
     assert_equal_int(keep, want, what=f"n={n}")
 
 
+@pytest.mark.parametrize("case", ["two_batches_dense_ids", "three_batches_many_tiny_classes", "zero_iou_suppresses",
+                                  "threshold_zero", "ids_256_to_16383", "ids_above_the_histogram", "id_255_and_256",
+                                  "sizes_63_to_66_and_129", "improper_boxes"])
+def test_nms_per_class_kernel_branches(case):
+    """nms_class.cu: every way through the per-class kernel (> 1000 candidates) against the oracle — the table-driven
+    class split (ids < 256) and the counting / bitonic sorts behind it, one and several tile batches per CTA, ordered
+    and round-robin dealing, the ZERO_SUP pair test, the smallest threshold, class sizes around the 64-box block."""
+    g = torch.Generator().manual_seed(77)
+    thr = 0.6
+    if case == "two_batches_dense_ids":            # 9 classes x 900: 120 tiles each, the CTA with two of them needs 2 batches
+        boxes, scores, _ = W.crowd_candidates(8100, 9, seed=21, clusters=12)
+        classes = torch.arange(8100) % 9 + 1
+    elif case == "three_batches_many_tiny_classes":   # ~2 900 classes: > 136 one-tile classes per CTA
+        boxes, scores, _ = W.crowd_candidates(8192, 9, seed=22, clusters=6)
+        classes = torch.randint(5000, 8000, (8192,), generator=g)
+    elif case == "zero_iou_suppresses":
+        boxes, scores, classes = W.crowd_candidates(3000, 40, seed=23, clusters=30)
+        thr = -0.5
+    elif case == "threshold_zero":
+        boxes, scores, classes = W.crowd_candidates(3000, 40, seed=24, clusters=300, spread=60.0)
+        thr = 0.0
+    elif case == "ids_256_to_16383":
+        boxes, scores, classes = W.crowd_candidates(4000, 60, seed=25, clusters=20)
+        classes = classes * 250 + 300
+    elif case == "ids_above_the_histogram":
+        boxes, scores, classes = W.crowd_candidates(2500, 30, seed=26, clusters=20)
+        classes = classes * 3000 + 20000
+    elif case == "id_255_and_256":
+        boxes, scores, classes = W.crowd_candidates(2400, 3, seed=27, clusters=10)
+        classes = classes + 253
+    elif case == "sizes_63_to_66_and_129":
+        sizes = [63, 64, 65, 66, 128, 129, 1, 2, 700]
+        classes = torch.cat([torch.full((m,), i + 1) for i, m in enumerate(sizes)])
+        classes = classes[torch.randperm(classes.numel(), generator=g)]
+        boxes, scores, _ = W.crowd_candidates(classes.numel(), 3, seed=28, clusters=3)
+    else:                                          # inverted and empty boxes never suppress and are never suppressed
+        boxes, scores, classes = W.crowd_candidates(2000, 6, seed=29, clusters=6)
+        boxes[::5] = boxes[::5][:, [2, 3, 0, 1]]
+        boxes[1::11, 2:] = boxes[1::11, :2]
+    want = O.batched_nms(boxes, scores, classes, thr).numpy()
+    _, _, _, keep = run_nms(boxes, scores, classes.long(), thr)
+    assert_equal_int(keep, want, what=case)
+    assert 0 < keep.size < boxes.shape[0] or case == "zero_iou_suppresses"
+
+
 def test_nms_threshold_ragged_batch_and_clip():
     b0, s0, c0 = W.crowd_candidates(500, 5, seed=41, clusters=5)
     b1, s1, c1 = W.crowd_candidates(500, 5, seed=42, clusters=5)
