@@ -28,3 +28,14 @@ fn(buf, 64)
 t = list(buf)
 names = ["threshold + rank", "bin starts", "placement", "rank in bin", "gather", "nms boxes"]
 print("nms_prepare_kernel, image 0: " + " ".join(f"{n} +{(t[31 + i] - t[30 + i]) / 1965:.1f}us" for i, n in enumerate(names)))
+
+# the dense path (coordinate-trick images): 1 000 crowded candidates x 16 images
+crowd = [W.crowd_candidates(1000, 80, seed=500 + i) for i in range(16)]
+kb = torch.stack([c[0] for c in crowd]).cuda(); ks = torch.stack([c[1] for c in crowd]).cuda(); kc = torch.stack([c[2] for c in crowd]).cuda()
+for _ in range(3):
+    ops.batched_nms(kb, ks, kc, 0.05, 0.6)
+torch.cuda.synchronize()
+fn(buf, 64)
+t = list(buf)
+print("dense path, image 0: nms_prepare_kernel " + " ".join(f"{n} +{(t[31 + i] - t[30 + i]) / 1965:.1f}us" for i, n in enumerate(names)))
+print("  scan kernel: " + " ".join(f"{n} +{(t[17 + i] - t[16 + i]) / 1965:.1f}us" for i, n in enumerate(["rows staged", "greedy pass", "outputs"])))
