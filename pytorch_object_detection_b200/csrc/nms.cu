@@ -335,11 +335,30 @@ nms_scan_smem_kernel(const CandSet set, const int wblocks, const int cap_pad,
       }
       if (lane == 0) keepw[rb] = keep;
       const bool k0 = (keep >> lane) & 1ull, k1 = (keep >> (lane + 32)) & 1ull;
-      for (unsigned m = flags & ~((2u << rb) - 1u); m; m &= m - 1u) {     // flagged column blocks ahead
-        const int w = __ffs((int)m) - 1;
-        const unsigned long long* col = sm + col_off(w) + rb * kNmsTile;
-        const unsigned long long v = warp_or64((k0 ? col[lane] : 0ull) | (k1 ? col[lane + 32] : 0ull));
-        if (lane == w) myrem |= v;
+      // flagged column blocks ahead, four at a time: one at a time the loop was a chain of dependent latencies (find
+      // the bit, address, two loads, two warp reductions: ~0.12 us per column block, 0.9 of the 1.4 us a crowded
+      // row block cost); four independent chains overlap
+      for (unsigned m = flags & ~((2u << rb) - 1u); m;) {
+        int w[4];
+        unsigned long long v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          w[q] = m ? __ffs((int)m) - 1 : -1;
+          m &= m - 1u;                                         // (0 stays 0)
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[q] = 0ull;
+          if (w[q] >= 0) {
+            const unsigned long long* col = sm + col_off(w[q]) + rb * kNmsTile;
+            v[q] = (k0 ? col[lane] : 0ull) | (k1 ? col[lane + 32] : 0ull);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const unsigned long long r = warp_or64(v[q]);
+          if (lane == w[q]) myrem |= r;
+        }
       }
     }
     // exclusive prefix of kept counts per block

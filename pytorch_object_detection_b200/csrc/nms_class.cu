@@ -397,7 +397,8 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
           const bool k0 = (keep >> lane) & 1ull, k1 = (keep >> (lane + 32)) & 1ull;
           if (k0) keep_rank(rank_of(s0 + rb * kNmsTile + lane));
           if (k1) keep_rank(rank_of(s0 + rb * kNmsTile + lane + 32));
-          for (int cb = rb + 1; cb < W; ++cb) {
+#pragma unroll 4
+          for (int cb = rb + 1; cb < W; ++cb) {                 // (independent chains of loads and warp reductions)
             const unsigned long long* col = buf + (size_t)(tile + cb - rb) * kNmsTile;
             const unsigned long long v = warp_or64((k0 ? col[lane] : 0ull) | (k1 ? col[lane + 32] : 0ull));
             if (lane == cb) myrem |= v;
