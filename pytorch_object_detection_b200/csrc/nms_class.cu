@@ -67,6 +67,7 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
   __shared__ unsigned short s_roff[kTileBudget];                // first tile row of the batch's classes in s_done
   __shared__ int s_done[kTileBudget];                           // units of pair tests finished, per tile row of a class
   __shared__ int s_queue[3];                                    // next unit, next class to be resolved, early passes
+  __shared__ int s_batch[4];                                    // classes, tiles, boxes, tile rows of the batch
   __shared__ unsigned short s_ord[kOrderMax];                   // classes by size, largest first
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   cg::cluster_group cluster = cg::this_cluster();
@@ -113,6 +114,7 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
   reinterpret_cast<uint4*>(wcnt)[tid] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < kwords; i += kClassThreads) keepbits[i] = 0u;
   __syncthreads();
+  B200DET_STAMP_NOSYNC(21);
   constexpr int kGroupsPerWarp = B200DET_MAX_BOX / 32 / kClassWarps;   // 8
   const int gpw = ((n + 31) / 32 + kClassWarps - 1) / kClassWarps;     // groups per warp in this image
   int cls_q[kGroupsPerWarp];
@@ -124,6 +126,10 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
     cls_q[q] = (q < gpw && i < n) ? set.cls[o0 + i] : 0;
   }
   unsigned short* wrow = wcnt + warp * kDenseClasses;
+#ifdef B200DET_TRACE
+  if (cls_q[0] == 0x7fffffff) g_trace[50] = 1;                  // (waits for the first load)
+  B200DET_STAMP_NOSYNC(22);
+#endif
 #pragma unroll
   for (int q = 0; q < kGroupsPerWarp; ++q) {
     if (q >= gpw) { cls_q[q] = -1; continue; }                   // (uniform over the CTA)
@@ -150,6 +156,7 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
     cls_q[q] = ok ? c : -1;
     loc_q[q] = (unsigned short)(base + r);
   }
+  B200DET_STAMP_NOSYNC(23);
   const bool bad_class = __syncthreads_or(cmax) != 0;            // also the barrier after the counts
   const bool dense = __syncthreads_or(sparse) == 0;
   B200DET_STAMP(1);
@@ -284,6 +291,7 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
     s_ord[before] = (unsigned short)tid;
   }
   __syncthreads();
+  B200DET_STAMP_NOSYNC(24);
   auto my_segment = [&](const int j) {                          // the j-th class of this CTA
     return ordered ? (int)s_ord[j * kClassCluster + ((j & 1) ? kClassCluster - 1 - rank : rank)] : rank + j * kClassCluster;
   };
@@ -305,34 +313,62 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
   float4* sbox = cbox_all;                                       // [kBoxBudget + 64] the batch's boxes, class after class
   float* sarea = carea_all;                                      // [kBoxBudget + 64]
   for (int j0 = 0; j0 < my_n;) {
-    int cnt = 0, tiles = 0, boxes = 0, rows = 0;                 // the batch: classes j0 .. j0 + cnt - 1
-    while (j0 + cnt < my_n && cnt < kTileBudget) {
-      const int sg = my_segment(j0 + cnt);
-      const int s0 = seg[sg], size = (sg + 1 < n_seg ? (int)seg[sg + 1] : n) - s0;
-      const int W = (size + kNmsTile - 1) / kNmsTile;            // 1 .. 16 blocks
-      const int t = W * (W + 1) / 2;
-      if (tiles + t > kTileBudget || boxes + size > kBoxBudget) break;   // (a class alone always fits)
-      if (tid == 0) {
+    // the batch: classes j0 .. j0 + cnt - 1, as many as fit the tile and the box budget.  Warp 0 builds the tables, a
+    // class per lane with warp scans (every thread walking the classes one by one kept all 32 warps busy for 1.6 us).
+    if (warp == 0) {
+      int cnt = 0, tiles = 0, boxes = 0, rows = 0;
+      for (bool more = true; more;) {
+        const int j = j0 + cnt + lane;
+        const bool have = j < my_n && cnt + lane < kTileBudget;
+        int s0 = 0, size = 0;
+        if (have) {
+          const int sg = my_segment(j);
+          s0 = seg[sg];
+          size = (sg + 1 < n_seg ? (int)seg[sg + 1] : n) - s0;
+        }
+        const int W = (size + kNmsTile - 1) / kNmsTile;          // 1 .. 16 blocks (0: no class)
+        const int t = W * (W + 1) / 2;
+        int it = t, ib = size, ir = W;                           // inclusive scans over the lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int ot = __shfl_up_sync(0xffffffffu, it, d), ob = __shfl_up_sync(0xffffffffu, ib, d);
+          const int orw = __shfl_up_sync(0xffffffffu, ir, d);
+          if (lane >= d) { it += ot; ib += ob; ir += orw; }
+        }
+        const bool fits = have && tiles + it <= kTileBudget && boxes + ib <= kBoxBudget;   // (a class alone always fits)
+        const unsigned ok = __ballot_sync(0xffffffffu, fits);
+        const int take = __ffs((int)~ok) - 1 < 0 ? 32 : __ffs((int)~ok) - 1;               // leading lanes that fit
+        if (lane < take) {
+          s_toff[cnt + lane] = (unsigned short)(tiles + it - t);
+          s_boff[cnt + lane] = (unsigned short)(boxes + ib - size);
+          s_s0[cnt + lane] = (unsigned short)s0;
+          s_roff[cnt + lane] = (unsigned short)(rows + ir - W);
+        }
+        const int last = max(take - 1, 0);
+        const int at = __shfl_sync(0xffffffffu, it, last), ab = __shfl_sync(0xffffffffu, ib, last);
+        const int ar = __shfl_sync(0xffffffffu, ir, last);
+        if (take > 0) { tiles += at; boxes += ab; rows += ar; }
+        cnt += take;
+        more = take == 32 && j0 + cnt < my_n && cnt < kTileBudget;
+      }
+      if (lane == 0) {
         s_toff[cnt] = (unsigned short)tiles;
         s_boff[cnt] = (unsigned short)boxes;
-        s_s0[cnt] = (unsigned short)s0;
-        s_roff[cnt] = (unsigned short)rows;
+        s_batch[0] = cnt;
+        s_batch[1] = tiles;
+        s_batch[2] = boxes;
+        s_batch[3] = rows;
+        s_queue[0] = 0;                                          // next unit
+        s_queue[1] = 0;                                          // next class to be resolved
+        s_queue[2] = 0;                                          // greedy passes running ahead of their class's tiles
       }
-      tiles += t;
-      boxes += size;
-      rows += W;
-      ++cnt;
     }
-    if (tid == 0) {
-      s_toff[cnt] = (unsigned short)tiles;
-      s_boff[cnt] = (unsigned short)boxes;
-      s_queue[0] = 0;                                            // next unit
-      s_queue[1] = 0;                                            // next class to be resolved
-      s_queue[2] = 0;                                            // greedy passes running ahead of their class's tiles
-    }
+    __syncthreads();
+    const int cnt = s_batch[0], tiles = s_batch[1], boxes = s_batch[2], rows = s_batch[3];
     for (int i = tid; i < rows; i += kClassThreads) s_done[i] = 0;
     for (int i = tid; i < tiles * kNmsTile; i += kClassThreads) tmask[i] = 0ull;
     __syncthreads();
+    if (j0 == 0) { B200DET_STAMP_NOSYNC(25); }
     // class of the batch that holds box / tile number v of the batch (offsets in `off`)
     auto class_of = [&](const unsigned short* off, const int v) {
       int lo = 0, hi = cnt;                                      // off[lo] <= v < off[hi]
@@ -349,6 +385,7 @@ nms_class_kernel(const CandSet set, const float thr_up, const int clip_h, const 
       sarea[i] = __fmul_rn(__fsub_rn(v.z, v.x), __fsub_rn(v.w, v.y));
     }
     __syncthreads();
+    if (j0 == 0) { B200DET_STAMP_NOSYNC(26); }
     const int units = tiles * kParts;
     volatile int* queue = s_queue;
     volatile int* done = s_done;

@@ -18,6 +18,10 @@ names = ["keys", "sort", "segments", "class warps", "write"]
 print(" ".join(f"{n} +{(t[i + 1] - t[i]) / 1965:.1f}us" for i, n in enumerate(names)), "segments", t[8])
 if t[11]:
     print(f"first batch of CTA 0 ({t[12]} tiles of {t[13]} classes): done +{(t[11] - t[3]) / 1965:.1f}us; all batches +{(t[14] - t[3]) / 1965:.1f}us")
+if t[21]:
+    d = lambda a, b: (t[b] - t[a]) / 1965
+    print(f"  class split: tables cleared +{d(0, 21):.1f}us, class ids loaded +{d(21, 22):.1f}us, counted +{d(22, 23):.1f}us, barriers +{d(23, 1):.1f}us; "
+          f"setup: dealing order +{d(3, 24):.1f}us, batch tables + clear +{d(24, 25):.1f}us, boxes staged +{d(25, 26):.1f}us")
 if t[15]:
     rel = lambda i: (t[i] - t[3]) / 1965
     print(f"  CTA 0: first unit taken at {rel(20):.1f}us, last unit taken at {rel(19):.1f}us; greedy pass of the largest class {rel(15):.1f} -> {rel(16):.1f}us, "
