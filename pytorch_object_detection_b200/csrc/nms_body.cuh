@@ -180,7 +180,7 @@ __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int s
 // The walk is a dependency chain, so it is written for the shortest one: row i only matters through the boxes AFTER
 // it (bits > i; lower bits are decided already), so bit i of the removed set is final when step i reads it and the
 // kept rows are simply the valid rows not removed at the end; rows past `valid` are zeroed before the walk; rows
-// 32-63 only touch the high word.  What is left per step is one bit test and one predicated OR (~15 cycles; the
+// 32-63 only touch the high word.  What is left per step is one bit test, one select and one OR (~15 cycles; the
 // shuffles that fetch the rows do not depend on the chain and run ahead) — the straightforward loop (alive flag from
 // valid and removed, select, OR, keep mask) was four dependent instructions and ~39 cycles per row, 1.3 us per block.
 // (Walking only the kept rows — next = lowest row neither removed nor visited — was measured and is SLOWER: its
