@@ -167,20 +167,15 @@ __device__ __forceinline__ SelectResult select_topk_cta(const LevelTable& lt, co
           B200DET_STAMP_NOSYNC(23);
           unsigned long long* tmp = sortbuf;                    // unordered inside a bin
           unsigned long long* fin = sortbuf + kSelThreads;
-          // (four independent atomics in flight at a time: their ~100-cycle round trips overlap)
+          // (at most kSelThreads of the ~24 x kSelThreads keys are selected — one per thread on average — so a branch
+          // per key beats keeping four atomics in flight: two instructions for a key that is not taken instead of ten)
 #pragma unroll
-          for (int j0 = 0; j0 < kSelItems; j0 += 4) {
-            unsigned at[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const uint32_t k_ = key[j0 + u];
-              at[u] = (k_ >= T && k_) ? atomicAdd(&hist[hist_slot(hist_bin(k_))], 1u) : 0xffffffffu;
+          for (int j = 0; j < kSelItems; ++j) {
+            const uint32_t k_ = key[j];
+            if (k_ >= T) {                                      // (T >= 1 and the invalid keys are 0)
+              const unsigned at = atomicAdd(&hist[hist_slot(hist_bin(k_))], 1u);
+              tmp[at] = ((unsigned long long)k_ << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(tid + j * kSelThreads));
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (at[u] != 0xffffffffu)
-                tmp[at[u]] = ((unsigned long long)key[j0 + u] << 32) |
-                             (unsigned long long)(0xffffffffu - (uint32_t)(tid + (j0 + u) * kSelThreads));
           }
           __syncthreads();
           B200DET_STAMP_NOSYNC(24);
