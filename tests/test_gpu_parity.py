@@ -206,6 +206,40 @@ def test_nms_per_class_kernel_branches(case):
     assert 0 < keep.size < boxes.shape[0] or case == "zero_iou_suppresses"
 
 
+def test_nms_per_class_kernel_pairs_at_the_threshold():
+    """The per-class kernel decides most pairs from two rounded products and leaves a band of one or two ulps around
+    the threshold to the exact test (csrc/nms_body.cuh mask_rows2_part).  Here hundreds of same-class pairs sit IN that
+    band: a box and a box it contains, whose IoU is h / side with h walked a few ulps around 0.6 * side, on three
+    scales; the kept set must be the oracle's (torchvision's fp32 quotient compared with the double threshold)."""
+    g = torch.Generator().manual_seed(5)
+    boxes, scores, classes = [], [], []
+    k = 0
+    for side in (10.0, 20.0, 37.0):
+        for step in range(-4, 5):
+            for rep in range(12):
+                h = np.float32(0.6) * np.float32(side)
+                for _ in range(abs(step)):
+                    h = np.nextafter(h, np.float32(np.inf if step > 0 else -np.inf), dtype=np.float32)
+                x0, y0 = 64.0 * (k % 40), 64.0 * (k // 40)
+                boxes += [[x0, y0, x0 + side, y0 + side], [x0, y0, x0 + side, y0 + float(h)]]
+                scores += [0.9 - 1e-4 * k, 0.5 - 1e-4 * k]
+                classes += [1 + k % 3, 1 + k % 3]
+                k += 1
+    fb, fs, fc = W.crowd_candidates(900, 3, seed=31, clusters=40)
+    fb[:, [0, 2]] += 3000.0                                       # the crowd sits beside the constructed pairs
+    boxes = torch.cat([torch.tensor(boxes, dtype=torch.float32), fb])
+    scores = torch.cat([torch.tensor(scores, dtype=torch.float32), fs * 0.4])
+    classes = torch.cat([torch.tensor(classes), fc])
+    perm = torch.randperm(boxes.shape[0], generator=g)
+    boxes, scores, classes = boxes[perm], scores[perm], classes[perm]
+    assert boxes.shape[0] > 1000                                   # per-class branch
+    want = O.batched_nms(boxes, scores, classes, 0.6).numpy()
+    _, _, _, keep = run_nms(boxes, scores, classes.long(), 0.6)
+    assert_equal_int(keep, want, what="pairs at the threshold")
+    inside = np.isin(np.nonzero((perm < 2 * k).numpy())[0], want)  # both outcomes occur among the constructed boxes
+    assert inside.sum() > k and inside.sum() < 2 * k
+
+
 def test_nms_threshold_ragged_batch_and_clip():
     b0, s0, c0 = W.crowd_candidates(500, 5, seed=41, clusters=5)
     b1, s1, c1 = W.crowd_candidates(500, 5, seed=42, clusters=5)
