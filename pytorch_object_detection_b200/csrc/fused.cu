@@ -48,7 +48,9 @@ __device__ __forceinline__ bool suppresses(const float4 a, const float aarea, co
   return iou_reaches(inter, __fsub_rn(__fadd_rn(aarea, carea), inter), iou_midpoint(thr_up));   // == (double)ovr > thr
 }
 
-template <bool REG>
+// FROM_SET: the candidate rows come from the candidate set that nms_prepare_kernel wrote (the stand-alone batched_nms
+// entry, <= 1024 candidates) instead of from the select; everything after the select is the same code.
+template <bool REG, bool FROM_SET = false>
 __global__ void __launch_bounds__(kSelThreads, 1)
 fused_select_nms_kernel(const LevelTable lt, const float* __restrict__ score, const int16_t* __restrict__ cls0,
                         const float thr, const int max_box, const CandSet set, const float thr_up,
@@ -84,8 +86,26 @@ fused_select_nms_kernel(const LevelTable lt, const float* __restrict__ score, co
   sel_out.nms_box = nullptr;                                  // NMS boxes stay in registers / shared memory here
   // (the score histogram of the select lives where the suppression mask will be: 64 KB of the 68 KB)
   static_assert(kMaskWords * 8 >= (size_t)kHistBins * sizeof(unsigned), "histogram aliases the mask");
-  const SelectResult sel = select_topk_cta<REG>(lt, score, cls0, thr, max_box, sel_out, nullptr, b, sortbuf, true,
-                                                REG ? reinterpret_cast<unsigned*>(maskT) : nullptr, false);
+  SelectResult sel;
+  int mysrc = tid;                                            // what the keep output names: the candidate's row
+  if constexpr (FROM_SET) {
+    sel.count = min(set.count[b], kFusedMaxBox);
+    sel.box = make_float4(0.f, 0.f, 0.f, 0.f);
+    sel.cls = -1;
+    sel.score = 0.f;
+    float vmax = -CUDART_INF_F;
+    if (tid < sel.count) {
+      sel.box = reinterpret_cast<const float4*>(set.box)[o0 + tid];
+      sel.cls = set.cls[o0 + tid];
+      sel.score = set.score[o0 + tid];
+      mysrc = set.src[o0 + tid];                              // ... in the caller's thresholded list
+      vmax = fmaxf(fmaxf(sel.box.x, sel.box.y), fmaxf(sel.box.z, sel.box.w));
+    }
+    sel.max_coord = block_max(vmax, s_f);
+  } else {
+    sel = select_topk_cta<REG>(lt, score, cls0, thr, max_box, sel_out, nullptr, b, sortbuf, true,
+                               REG ? reinterpret_cast<unsigned*>(maskT) : nullptr, false);
+  }
   const int n = sel.count;
   const int W = (n + kNmsTile - 1) / kNmsTile;
   B200DET_STAMP(8);
@@ -195,11 +215,27 @@ fused_select_nms_kernel(const LevelTable lt, const float* __restrict__ score, co
       }
       if (lane == 0) keepw[rb] = keep;
       const bool k0 = (keep >> lane) & 1ull, k1 = (keep >> (lane + 32)) & 1ull;
-      for (unsigned m = flags & ~((2u << rb) - 1u); m; m &= m - 1u) {      // flagged column blocks ahead
-        const int w = __ffs((int)m) - 1;
-        const unsigned long long* col = maskT + col_off(w) + rb * kNmsTile;
-        const unsigned long long v = warp_or64((k0 ? col[lane] : 0ull) | (k1 ? col[lane + 32] : 0ull));
-        if (lane == w) myrem |= v;
+      for (unsigned m = flags & ~((2u << rb) - 1u); m;) {     // flagged column blocks ahead, four independent
+        int w[4];                                             //   chains of loads and warp reductions at a time
+        unsigned long long v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          w[q] = m ? __ffs((int)m) - 1 : -1;
+          m &= m - 1u;                                        // (0 stays 0)
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[q] = 0ull;
+          if (w[q] >= 0) {
+            const unsigned long long* col = maskT + col_off(w[q]) + rb * kNmsTile;
+            v[q] = (k0 ? col[lane] : 0ull) | (k1 ? col[lane + 32] : 0ull);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const unsigned long long r = warp_or64(v[q]);
+          if (lane == w[q]) myrem |= r;
+        }
       }
     }
     __syncwarp();
@@ -219,7 +255,7 @@ fused_select_nms_kernel(const LevelTable lt, const float* __restrict__ score, co
     const unsigned long long kw = keepw[tid >> 6];
     if ((kw >> (tid & 63)) & 1ull) {
       const int o = s_pre[tid >> 6] + __popcll(kw & ((1ull << (tid & 63)) - 1ull));
-      store_kept(set, out, o0, q0, tid, o, clip_h, clip_w, raw, sel.score, mycls, tid);
+      store_kept(set, out, o0, q0, tid, o, clip_h, clip_w, raw, sel.score, mycls, mysrc);
     }
   }
   B200DET_STAMP(11);
@@ -227,6 +263,24 @@ fused_select_nms_kernel(const LevelTable lt, const float* __restrict__ score, co
 }
 
 }  // namespace
+
+// the NMS half of the fused kernel on a candidate set made by nms_prepare_kernel (cap <= 1024, nms_thr >= 0)
+bool fused_nms_supported(int cap, double nms_thr) { return cap <= kFusedMaxBox && nms_thr >= 0.0; }
+
+int launch_fused_nms_from_set(const CandSet& set, int batch, double nms_thr, int clip_h, int clip_w, const NmsOut& out,
+                              cudaStream_t stream) {
+  float thr_up;
+  bool zero_sup;
+  nms_threshold_params(nms_thr, &thr_up, &zero_sup);
+  if (zero_sup || set.cap > kFusedMaxBox) return B200DET_ERR_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(fused_select_nms_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kFusedSmem);
+  if (e != cudaSuccess) { set_cuda_error(e); return B200DET_ERR_CUDA; }
+  LevelTable none = {};
+  fused_select_nms_kernel<true, true><<<batch, kSelThreads, kFusedSmem, stream>>>(none, nullptr, nullptr, 0.f, 0, set, thr_up,
+                                                                                 clip_h, clip_w, out);
+  return check_launch();
+}
 
 bool fused_supported(const LevelTable& lt, int max_box, double nms_thr) {
   const int k = max_box < lt.num_points ? max_box : lt.num_points;

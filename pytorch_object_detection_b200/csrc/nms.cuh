@@ -64,6 +64,11 @@ int launch_fused_select_nms(const LevelTable& lt, int batch, const float* score,
                             int max_box, const CandSet& set, double nms_thr, int clip_h, int clip_w,
                             const NmsOut& out, cudaStream_t stream);
 
+// the NMS half of that kernel alone, on a candidate set made by nms_prepare_kernel (cap <= 1024 and nms_thr >= 0)
+bool fused_nms_supported(int cap, double nms_thr);
+int launch_fused_nms_from_set(const CandSet& set, int batch, double nms_thr, int clip_h, int clip_w, const NmsOut& out,
+                              cudaStream_t stream);
+
 // candidate set + suppression mask carved out of one caller-owned workspace
 size_t nms_set_workspace_bytes(int batch, int cap);
 void nms_set_carve(void* base, int batch, int cap, CandSet* set, unsigned long long** mask);

@@ -43,3 +43,10 @@ fn(buf, 64)
 t = list(buf)
 print("dense path, image 0: nms_prepare_kernel " + " ".join(f"{n} +{(t[31 + i] - t[30 + i]) / 1965:.1f}us" for i, n in enumerate(names)))
 print("  scan kernel: " + " ".join(f"{n} +{(t[17 + i] - t[16 + i]) / 1965:.1f}us" for i, n in enumerate(["rows staged", "greedy pass", "outputs"])))
+fn2 = lib.b200det_debug_read_trace_fused
+fn2.argtypes = [C.c_void_p, C.c_int]
+fn2(buf, 64)
+t = list(buf)
+if t[8]:
+    seq = [(8, "set loaded"), (12, "zero-fill + stage"), (13, "buckets"), (9, "pair tests"), (10, "greedy pass"), (11, "outputs")]
+    print("  bucket path (NMS half of the fused kernel), image 0: " + " ".join(f"{nm} +{(t[b] - t[a]) / 1965:.1f}us" for (a, _), (b, nm) in zip(seq, seq[1:])))

@@ -240,6 +240,30 @@ def test_nms_per_class_kernel_pairs_at_the_threshold():
     assert inside.sum() > k and inside.sum() < 2 * k
 
 
+@pytest.mark.parametrize("n,ncls,clusters,thr", [(1000, 80, 50, 0.6), (1024, 3, 4, 0.5), (700, 1, 2, 0.3), (64, 2, 1, 0.6),
+                                                 (1, 1, 1, 0.6), (999, 20, 300, 0.0)])
+def test_standalone_nms_bucket_path_equals_dense_chain(n, ncls, clusters, thr, monkeypatch):
+    """b200det_batched_nms with <= 1024 candidates runs the NMS half of the fused head kernel on the prepared set;
+    B200DET_DENSE_NMS=1 forces the dense mask + scan kernels.  Same outputs, and the oracle's keep indices; boxes with
+    negative corners (cross-class suppression under the coordinate trick) included."""
+    boxes, scores, classes = zip(*[W.crowd_candidates(n, ncls, seed=700 + i, clusters=clusters) for i in range(3)])
+    boxes, scores, classes = torch.stack(boxes), torch.stack(scores), torch.stack(classes)
+    boxes[:, ::9] -= 500.0
+    in_count = torch.tensor([n, max(n // 2, 1), n], dtype=torch.int32)
+    args = (boxes.to(DEV), scores.to(DEV), classes.to(DEV), 0.1, thr, in_count.to(DEV), (832, 1344))
+    got = ops.batched_nms(*args)
+    monkeypatch.setenv("B200DET_DENSE_NMS", "1")
+    ref = ops.batched_nms(*args)
+    assert torch.equal(got[4], ref[4])
+    for i in range(3):
+        m = int(ref[4][i])
+        for a, b in zip(got[:4], ref[:4]):
+            assert torch.equal(a[i, :m], b[i, :m])
+        cnt = int(in_count[i])
+        want = O.post_process_image(scores[i, :cnt], classes[i, :cnt], boxes[i, :cnt], 0.1, thr)
+        assert_equal_int(to_np(got[3][i, :m]), to_np(want[3]), what=f"keep img {i}")
+
+
 def test_nms_threshold_ragged_batch_and_clip():
     b0, s0, c0 = W.crowd_candidates(500, 5, seed=41, clusters=5)
     b1, s1, c1 = W.crowd_candidates(500, 5, seed=42, clusters=5)
@@ -1141,10 +1165,11 @@ def test_full_size_config4_dense_crowd():
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("ncls,crowded,seed,max_box", [(3, True, 51, 1000), (80, True, 52, 1000), (1, True, 53, 1000),
                                                        (20, False, 54, 1024), (5, True, 55, 300)])
-def test_fused_postprocess_equals_dense_stage_chain(ncls, crowded, seed, max_box):
+def test_fused_postprocess_equals_dense_stage_chain(ncls, crowded, seed, max_box, monkeypatch):
     """Crowded boxes (many same-class overlaps) and large boxes around the top-left corner (negative
     x1, y1: the cross-class 'wildcard' case of the coordinate trick).  The fused kernel must give
-    exactly what K1 -> K2 -> dense NMS (stand-alone entry) and the oracle give."""
+    exactly what K1 -> K2 -> dense NMS (stand-alone entry, dense mask + scan kernels forced) and the oracle give."""
+    monkeypatch.setenv("B200DET_DENSE_NMS", "1")
     x = W.head_outputs(2, ncls, W.VOC_LEVELS, seed=seed, crowded=crowded)
     for lv in range(len(x[2])):
         x[2][lv][:, :2, :3, :3] += 300.0           # l, t huge near the corner -> x1, y1 << -1 (wildcards)
