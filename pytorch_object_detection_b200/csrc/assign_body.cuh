@@ -112,42 +112,6 @@ __device__ __forceinline__ bool window_point_positive(const GtEntry& g, const in
   return true;
 }
 
-// The same test with the window anchored at floor(cx * inv_s): 1 / s as a multiplication (one cell of slack in
-// hwin covers the difference to the division for strides that are not powers of two).
-__device__ __forceinline__ bool window_point_positive_mul(const GtEntry& g, const int k, const int hwin, const int s,
-                                                          const float inv_s, const int w, const int h, const float lo,
-                                                          const float hi, const float radius, int* pos, float* area) {
-  const int wside = 2 * hwin + 1;
-  const int half = s / 2;
-  const int kr = k / wside;
-  const int j = (int)floorf(g.cx * inv_s) + (k - kr * wside) - hwin;
-  const int i = (int)floorf(g.cy * inv_s) + kr - hwin;
-  if (j < 0 || j >= w || i < 0 || i >= h) return false;
-  const float x = (float)(j * s + half), y = (float)(i * s + half);
-  const float cmax = fmaxf(fabsf(__fsub_rn(x, g.cx)), fabsf(__fsub_rn(y, g.cy)));
-  if (!(cmax < radius)) return false;
-  const float lf = __fsub_rn(x, g.x0), tf = __fsub_rn(y, g.y0);
-  const float rf = __fsub_rn(g.x1, x), bf = __fsub_rn(g.y1, y);
-  const float omin = fminf(fminf(lf, tf), fminf(rf, bf));
-  const float omax = fmaxf(fmaxf(lf, tf), fmaxf(rf, bf));
-  if (!((omin > 0.f) && (omax > lo) && (omax <= hi))) return false;
-  *pos = i * w + j;
-  *area = __fmul_rn(__fadd_rn(lf, rf), __fadd_rn(tf, bf));
-  return true;
-}
-
-// The vote of a positive pair whose point lies in [t0, t1] of this level: a 64-bit atomicMin on
-// (area bits, GT index) = smallest area, lowest index on ties.  keys is indexed by pos - t0.
-__device__ __forceinline__ void window_vote(const GtEntry& g, const int k, const int hwin, const int s, const int w,
-                                            const int h, const int t0, const int t1, const float lo, const float hi,
-                                            const float radius, unsigned long long* keys) {
-  int pos;
-  float area;
-  if (!window_point_positive(g, k, hwin, s, w, h, lo, hi, radius, &pos, &area)) return;
-  if (pos < t0 || pos > t1) return;
-  atomicMin(&keys[pos - t0], ((unsigned long long)__float_as_uint(area) << 32) | (unsigned)g.idx);
-}
-
 // Targets of a positive point (col, row) of a level with this stride, assigned to box g.
 __device__ __forceinline__ void positive_targets(const GtEntry& g, const int col, const int row, const int s,
                                                  float4* reg, float* cnt) {

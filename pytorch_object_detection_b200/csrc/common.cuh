@@ -259,9 +259,6 @@ __device__ __forceinline__ void stg_stream_f4(float* p, float4 v) {
 __device__ __forceinline__ void stg_stream_f1(float* p, float v) {
   asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
-__device__ __forceinline__ void stg_stream_s64(long long* p, long long v) {
-  asm volatile("st.global.cs.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 // level of a level-major point index / of a tile index (branch-free over the small table)
 __device__ __forceinline__ int level_of_point(const LevelTable& t, int p) {
